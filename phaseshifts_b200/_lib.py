@@ -1,0 +1,89 @@
+"""ctypes binding of ``libphsh_b200.so`` (the C ABI declared in ``include/phsh_b200.h``).
+
+The shared library is built in-tree by ``phaseshifts_b200.build`` (``nvcc`` for
+``sm_100a``).  There is no CPU fallback: if the library is missing, or no B200 is
+visible, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libphsh_b200.so")
+
+OK, EINVAL, ENODEV, ECUDA, EIO, ENOMEM = 0, -1, -2, -3, -4, -5
+ASBUILT, UNWRAP, FAST, REAL32, NONREL = 0x1, 0x2, 0x4, 0x8, 0x10
+
+XS_DEFAULT = -9.03065133  # libphsh.f:4760
+DX_DEFAULT = 3.125e-2  # libphsh.f:4761
+
+
+class PhshB200Error(RuntimeError):
+    """A libphsh_b200 call failed (code, message)."""
+
+    def __init__(self, code, msg):
+        super().__init__("libphsh_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class RelOpts(C.Structure):
+    _fields_ = [("xs", C.c_double), ("dx", C.c_double), ("lsm", C.c_int), ("flags", C.c_int)]
+
+
+class FileOpts(C.Structure):
+    _fields_ = [("flags", C.c_int), ("max_energies", C.c_int), ("max_jri", C.c_int), ("device", C.c_int)]
+
+
+_dp = C.c_void_p  # raw addresses (host numpy or device tensor data_ptr)
+_SIGNATURES = {
+    "phsh_b200_last_error": (C.c_char_p, []),
+    "phsh_b200_version": (C.c_char_p, []),
+    "phsh_b200_device_count": (C.c_int, []),
+    "phsh_b200_rel_batch_device": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_long, C.c_int,
+                                             C.POINTER(RelOpts), _dp, _dp, _dp, C.c_void_p]),
+    "phsh_b200_rel_batch_host": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_long, C.c_int,
+                                           C.POINTER(RelOpts), _dp, _dp, _dp, C.c_int]),
+    "phsh_b200_conphas_device": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_void_p]),
+    "phsh_b200_conphas_host": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int]),
+    "phsh_b200_cav_batch_device": (C.c_int, [_dp, _dp, C.c_long, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int,
+                                             _dp, C.c_void_p]),
+    "phsh_b200_cav_batch_host": (C.c_int, [_dp, _dp, C.c_long, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int,
+                                           _dp, C.c_int]),
+    "phsh_b200_wil_batch_device": (C.c_int, [_dp, _dp, C.c_long, _dp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, _dp, C.c_void_p]),
+    "phsh_b200_wil_batch_host": (C.c_int, [_dp, _dp, C.c_long, _dp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, _dp, C.c_int]),
+    "phsh_b200_rel_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FileOpts)]),
+    "phsh_b200_cav_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FileOpts)]),
+    "phsh_b200_wil_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FileOpts)]),
+    "phsh_b200_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_LIB = None
+
+
+def load():
+    """Load the CUDA library; raise loudly (never fall back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise PhshB200Error(ENODEV, "%s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                        "(nvcc, sm_100a); there is no CPU fallback" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise PhshB200Error(rc, load().phsh_b200_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return int(load().phsh_b200_device_count())

@@ -1,0 +1,204 @@
+"""Batched tensor API over the C ABI (``include/phsh_b200.h``).
+
+Device tensors (``torch`` CUDA, float64) go through the ``*_device`` entry points on
+torch's current stream and return device tensors; host arrays (numpy / CPU tensors)
+go through the ``*_host`` entry points, which do the H2D/D2H copies themselves.
+torch is only the plumbing for memory and streams -- all arithmetic is in
+``libphsh_b200.so``.  Nothing here can run without a B200: there is no CPU path.
+
+Reference semantics mirrored (paths relative to the reference checkout):
+``phsh_rel_batch``  <- PHSH_REL / DLGKAP / SBFIT   phaseshifts/lib/libphsh.f:4552-4946
+``phsh_cav_batch``  <- PHSH_CAV / PS / CALCBF      phaseshifts/lib/libphsh.f:3585-3887
+``phsh_wil_batch``  <- PHSH_WIL / S16 / S10 / S5   phaseshifts/lib/libphsh.f:3893-4500
+``conphas``         <- Conphas.calculate           phaseshifts/conphas.py:437-456
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ASBUILT, FAST, NONREL, REAL32, UNWRAP, DX_DEFAULT, XS_DEFAULT
+
+_F32_13_6 = float(np.float32(13.6))  # the REAL*4 literal 13.6 of PHSH_REL (libphsh.f:4639-4641)
+
+
+def rel_energy_grid(es_ev, de_ev, ue_ev, max_energies=250, asbuilt=False):
+    """Energy bookkeeping of PHSH_REL (libphsh.f:4625-4667, 4674-4693), in IEEE double like the Fortran.
+
+    Returns ``dict(e_l0, e_l, e_ev, n_header, es, de)``: Rydberg energies seen by the l=0 loop and by
+    the l>=1 loops, the eV values ENERG() printed in ``phasout`` and the N written in its header
+    (before the 250 cap, as the Fortran does).
+    """
+    es, de, ue = float(es_ev), float(de_ev), float(ue_ev)
+    if not de > 0.0:
+        es, de, ue = -0.5, 0.025, 1.0
+    n = int((ue - es) / de + 0.5) + 1
+    n_header = n
+    es_h, de_h = es, de
+    es, de = es / _F32_13_6, de / _F32_13_6
+    if max_energies and max_energies > 0 and n > max_energies:
+        n = max_energies
+    n = max(n, 0)
+    e_l0, e_l, e_ev = np.empty(n), np.empty(n), np.empty(n)
+    e = es
+    for j in range(n):
+        e_l0[j] = e
+        e = e * _F32_13_6
+        e_ev[j] = e
+        e = e / _F32_13_6
+        e = e + de
+    e = es
+    for j in range(n):
+        e_l[j] = e
+        if not asbuilt:  # phsh2.f:884-886 round trip, dropped in libphsh.f:4693
+            e = e * _F32_13_6
+            e = e / _F32_13_6
+        e = e + de
+    return dict(e_l0=e_l0, e_l=e_l, e_ev=e_ev, n_header=n_header, es=es_h, de=de_h)
+
+
+def _flags(unwrap=False, asbuilt=False, fast=False, real32=False, nonrel=False):
+    return ((UNWRAP if unwrap else 0) | (ASBUILT if asbuilt else 0) | (FAST if fast else 0) |
+            (REAL32 if real32 else 0) | (NONREL if nonrel else 0))
+
+
+def _is_cuda_tensor(x):
+    try:
+        import torch
+    except ImportError:  # pragma: no cover
+        return False
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _np64(x):
+    try:
+        import torch
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+    except ImportError:  # pragma: no cover
+        pass
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def _np32i(x, n):
+    try:
+        import torch
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+    except ImportError:  # pragma: no cover
+        pass
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.int32), (n,)))
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else C.c_void_p(a.data_ptr())
+
+
+def phsh_rel_batch(pot, jri, energies_ryd, lmax, *, energies_l0=None, xs=XS_DEFAULT, dx=DX_DEFAULT, unwrap=False,
+                   asbuilt=False, fast=False, real32=False, nonrel=False, per_kappa=False, counters=False,
+                   device=0, out=None):
+    """Relativistic phase shifts for a batch of muffin-tin potentials.
+
+    pot           [P, J]   r*V(r) in Ryd*bohr on r_j = exp(xs + (j-1) dx) (any sign, |.| is taken)
+    jri           [P]      radial points per potential (7 <= jri <= J)
+    energies_ryd  [NE] or [P, NE]  energies (Rydberg) used by the l>=1 loops; ``energies_l0`` (same shape,
+                  default: the same array) by the l=0 loop (see ``rel_energy_grid``)
+    returns delta [P, NE, lmax+1] (same kind of container as ``pot``); with ``per_kappa`` also the raw
+    per-kappa phases [P, lmax+1, NE, 2]; with ``counters`` also {calls, milne_steps, corr_evals, flops}.
+    """
+    lib = _lib.load()
+    opts = _lib.RelOpts(float(xs), float(dx), int(lmax), _flags(unwrap, asbuilt, fast, real32, nonrel))
+    L1 = int(lmax) + 1
+    if _is_cuda_tensor(pot):
+        import torch
+        if pot.dtype != torch.float64 or pot.dim() != 2 or not pot.is_contiguous():
+            raise ValueError("pot must be a contiguous float64 [P, J] tensor")
+        dev = pot.device
+        P, J = pot.shape
+        if J % 2:
+            pot = torch.nn.functional.pad(pot, (0, 1)).contiguous()
+            J += 1
+        jri_t = torch.as_tensor(jri, dtype=torch.int32, device=dev).expand(P).contiguous()
+        e_l = torch.as_tensor(energies_ryd, dtype=torch.float64, device=dev).contiguous()
+        e_l0 = e_l if energies_l0 is None else torch.as_tensor(energies_l0, dtype=torch.float64, device=dev).contiguous()
+        NE = e_l.shape[-1]
+        e_stride = 0 if e_l.dim() == 1 else NE
+        if e_l.dim() == 2 and e_l.shape[0] != P:
+            raise ValueError("per-potential energies must be [P, NE]")
+        delta = out if out is not None else torch.empty((P, NE, L1), dtype=torch.float64, device=dev)
+        kap = torch.empty((P, L1, NE, 2), dtype=torch.float64, device=dev) if per_kappa else None
+        cnt = torch.zeros(4, dtype=torch.int64, device=dev) if counters else None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.phsh_b200_rel_batch_device(
+                _ptr(pot), J, _ptr(jri_t), P, _ptr(e_l0), _ptr(e_l), e_stride, NE, C.byref(opts), _ptr(delta),
+                _ptr(kap) if per_kappa else None, _ptr(cnt) if counters else None, C.c_void_p(stream)))
+        res = [delta]
+        if per_kappa:
+            res.append(kap)
+        if counters:
+            c = cnt.cpu().numpy()
+            res.append(_counter_dict(c))
+        return res[0] if len(res) == 1 else tuple(res)
+    # host path
+    pot = _np64(pot)
+    if pot.ndim != 2:
+        raise ValueError("pot must be [P, J]")
+    P, J = pot.shape
+    jri_a = _np32i(jri, P)
+    e_l = _np64(energies_ryd)
+    e_l0 = e_l if energies_l0 is None else _np64(energies_l0)
+    NE = e_l.shape[-1]
+    e_stride = 0 if e_l.ndim == 1 else NE
+    delta = out if out is not None else np.empty((P, NE, L1))
+    kap = np.empty((P, L1, NE, 2)) if per_kappa else None
+    cnt = np.zeros(4, dtype=np.uint64)
+    _lib.check(lib.phsh_b200_rel_batch_host(_ptr(pot), J, _ptr(jri_a), P, _ptr(e_l0), _ptr(e_l), e_stride, NE,
+                                            C.byref(opts), _ptr(delta), _ptr(kap) if per_kappa else None,
+                                            _ptr(cnt), int(device)))
+    res = [delta]
+    if per_kappa:
+        res.append(kap)
+    if counters:
+        res.append(_counter_dict(cnt))
+    return res[0] if len(res) == 1 else tuple(res)
+
+
+def _counter_dict(c):
+    calls, steps, evals = int(c[0]), int(c[1]), int(c[2])
+    # as-written FP64 operation count: 5 RK steps x 64 + 10 per call, 23 per Milne step, 28 per corrector evaluation
+    return dict(calls=calls, milne_steps=steps, corr_evals=evals, flops=330.0 * calls + 23.0 * steps + 28.0 * evals)
+
+
+def conphas(phas, lmax=None, device=0):
+    """pi-jump removal along the energy axis (conphas.py:437-456).  phas [P, NE, L] or [NE, L]."""
+    lib = _lib.load()
+    squeeze = False
+    if _is_cuda_tensor(phas):
+        import torch
+        x = phas.contiguous()
+        if x.dim() == 2:
+            x, squeeze = x.unsqueeze(0), True
+        P, NE, L = x.shape
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.phsh_b200_conphas_device(_ptr(x), P, NE, L, L - 1 if lmax is None else int(lmax), _ptr(out),
+                                                    C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+        return out[0] if squeeze else out
+    x = _np64(phas)
+    if x.ndim == 2:
+        x, squeeze = x[None], True
+    P, NE, L = x.shape
+    out = np.empty_like(x)
+    _lib.check(lib.phsh_b200_conphas_host(_ptr(x), P, NE, L, L - 1 if lmax is None else int(lmax), _ptr(out), int(device)))
+    return out[0] if squeeze else out
+
+
+def fp64_peak(device=0):
+    """Measured FP64 DFMA peak (TFLOP/s) of one device and the SM clock it implies (MHz)."""
+    lib = _lib.load()
+    tf, mhz = C.c_double(), C.c_double()
+    _lib.check(lib.phsh_b200_fp64_peak(int(device), C.byref(tf), C.byref(mhz)))
+    return tf.value, mhz.value

@@ -1,0 +1,346 @@
+// phsh_b200.cu -- C-ABI entry points (include/phsh_b200.h) and launch logic for the sm_100a kernels.
+// There is deliberately no CPU implementation here: without a CUDA device every compute call fails.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "phsh_common.h"
+#include "phsh_rel.cuh"
+#include "phsh_cav.cuh"
+#include "phsh_wil.cuh"
+
+namespace phsh {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? PHSH_B200_ENODEV
+           : (e == cudaErrorMemoryAllocation)                            ? PHSH_B200_ENOMEM
+                                                                         : PHSH_B200_ECUDA;
+}
+
+int check_current_device() {
+    int dev = 0;
+    PHSH_CUDA(cudaGetDevice(&dev));
+    int major = 0;
+    PHSH_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        set_error("device %d has compute capability %d.x; this library is built for sm_100a (B200) only", dev, major);
+        return PHSH_B200_ENODEV;
+    }
+    return 0;
+}
+
+int select_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); libphsh_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return PHSH_B200_ENODEV;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device index %d out of range [0,%d)", device, n);
+        return PHSH_B200_EINVAL;
+    }
+    PHSH_CUDA(cudaSetDevice(device));
+    static std::once_flag pool_once[64];
+    if (device < 64)
+        std::call_once(pool_once[device], [device]() {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long thr = ~0ull;  // keep scratch cached between calls
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+        });
+    return check_current_device();
+}
+
+int DeviceBuf::alloc(size_t bytes, cudaStream_t stream) {
+    s = stream;
+    PHSH_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+static RelConsts make_rel_consts(const phsh_b200_rel_opts& o) {
+    RelConsts c;
+    memset(&c, 0, sizeof c);
+    const double HF = .5;
+    c.TS = std::exp(o.xs);
+    c.TDX = std::exp(o.dx);
+    c.DX2 = HF * o.dx;
+    c.X20 = static_cast<double>(0.3f) * o.dx;  // (.3)*DX with a REAL*4 literal (libphsh.f:4772)
+    c.XMFT = 4.4444444444444e-2 * o.dx;
+    c.CIN = (o.flags & PHSH_B200_NONREL) ? 0.0 : 1.3312581146e-5;
+    c.VCZ = 0.0;
+    double X = o.xs;
+    for (int n = 0; n < 5; ++n) {
+        double XC = X;
+        c.rk_t[n][0] = std::exp(XC);
+        XC = XC + c.DX2;
+        c.rk_t[n][1] = std::exp(XC);
+        XC = XC + c.DX2;
+        c.rk_t[n][2] = std::exp(XC);
+        X = X + o.dx;
+    }
+    c.T6 = std::exp(X);
+    c.lsm = o.lsm;
+    c.flags = o.flags;
+    return c;
+}
+
+template <bool FAST, class Real>
+static int launch_rel(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0, const double* e_l,
+                      long e_stride, int NE, const RelConsts& c, int jpad, double* raw, double* delta,
+                      unsigned long long* counters, cudaStream_t st) {
+    const int L1 = c.lsm + 1;
+    int block = NE >= 128 ? 128 : ((NE + 31) / 32) * 32;
+    const int chunks = (NE + block - 1) / block;
+    // enough CTAs to fill 148 SMs several times over; otherwise split the l range across CTAs
+    int lgroups = 1;
+    const long target = 148L * 8;
+    while (static_cast<long>(P) * chunks * lgroups < target && lgroups < L1) ++lgroups;
+    const size_t smem = static_cast<size_t>(2 * jpad) * sizeof(double) + 16;
+    auto kern = rel_integrate_kernel<FAST, Real>;
+    if (smem > 48 * 1024) PHSH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long grid = static_cast<long>(P) * lgroups * chunks;
+    kern<<<static_cast<unsigned>(grid), block, smem, st>>>(pot, pot_stride, jri, e_l0, e_l, e_stride, NE, c, lgroups,
+                                                            chunks, jpad, raw, counters);
+    PHSH_CUDA(cudaGetLastError());
+    const long warps = static_cast<long>(P) * L1;
+    rel_energy_axis_kernel<Real><<<static_cast<unsigned>((warps + 3) / 4), 128, 0, st>>>(
+        raw, P, L1, NE, (c.flags & PHSH_B200_UNWRAP) ? 1 : 0, delta);
+    PHSH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int rel_check(long pot_stride, int P, int NE, const phsh_b200_rel_opts* o) {
+    if (!o) {
+        set_error("opts is NULL");
+        return PHSH_B200_EINVAL;
+    }
+    if (P < 0 || NE < 0 || o->lsm < 0 || o->lsm > 63 || pot_stride < 7) {
+        set_error("bad sizes: P=%d NE=%d lsm=%d pot_stride=%ld", P, NE, o->lsm, pot_stride);
+        return PHSH_B200_EINVAL;
+    }
+    if (!(o->dx > 0.0) || !std::isfinite(o->xs)) {
+        set_error("bad radial grid xs=%g dx=%g", o->xs, o->dx);
+        return PHSH_B200_EINVAL;
+    }
+    if (static_cast<size_t>(2 * (pot_stride + 2)) * sizeof(double) + 16 > 200 * 1024) {
+        set_error("pot_stride=%ld does not fit the shared-memory staging buffer", pot_stride);
+        return PHSH_B200_EINVAL;
+    }
+    return 0;
+}
+
+}  // namespace phsh
+
+using namespace phsh;
+
+extern "C" {
+
+const char* phsh_b200_last_error(void) { return g_err.c_str(); }
+const char* phsh_b200_version(void) { return "phsh_b200 0.1 (sm_100a)"; }
+
+int phsh_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int phsh_b200_rel_batch_device(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0,
+                               const double* e_l, long e_stride, int NE, const phsh_b200_rel_opts* opts, double* delta,
+                               double* kappa_out, unsigned long long* counters, void* stream) {
+    int rc = rel_check(pot_stride, P, NE, opts);
+    if (rc) return rc;
+    if ((reinterpret_cast<uintptr_t>(pot) & 15) || (pot_stride & 1)) {
+        set_error("pot must be 16-byte aligned with an even pot_stride (TMA bulk copy)");
+        return PHSH_B200_EINVAL;
+    }
+    if (P == 0 || NE == 0) return 0;
+    rc = check_current_device();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!e_l) e_l = e_l0;
+    const RelConsts c = make_rel_consts(*opts);
+    const int L1 = opts->lsm + 1;
+    DeviceBuf scratch;
+    double* raw = kappa_out;
+    if (!raw) {
+        rc = scratch.alloc(static_cast<size_t>(P) * L1 * NE * 2 * sizeof(double), st);
+        if (rc) return rc;
+        raw = static_cast<double*>(scratch.p);
+    }
+    const int jpad = static_cast<int>((pot_stride + 1) & ~1L);
+    const bool fast = (opts->flags & PHSH_B200_FAST) != 0, r32 = (opts->flags & PHSH_B200_REAL32) != 0;
+    if (fast && r32)
+        return launch_rel<true, float>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, delta, counters, st);
+    if (fast)
+        return launch_rel<true, double>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, delta, counters, st);
+    if (r32)
+        return launch_rel<false, float>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, delta, counters, st);
+    return launch_rel<false, double>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, delta, counters, st);
+}
+
+int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0,
+                             const double* e_l, long e_stride, int NE, const phsh_b200_rel_opts* opts, double* delta,
+                             double* kappa_out, unsigned long long* counters, int device) {
+    int rc = rel_check(pot_stride, P, NE, opts);
+    if (rc) return rc;
+    for (int p = 0; p < P; ++p)
+        if (jri[p] < 7 || jri[p] > pot_stride) {
+            set_error("jri[%d]=%d outside [7, pot_stride=%ld]", p, jri[p], pot_stride);
+            return PHSH_B200_EINVAL;
+        }
+    rc = select_device(device);
+    if (rc) return rc;
+    if (P == 0 || NE == 0) return 0;
+    if (!e_l) e_l = e_l0;
+    cudaStream_t st;
+    PHSH_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard {
+        cudaStream_t s;
+        ~StreamGuard() { cudaStreamDestroy(s); }
+    } guard{st};
+    const int L1 = opts->lsm + 1;
+    const long ps = (pot_stride + 1) & ~1L;  // device copy padded to an even stride
+    const size_t n_e = e_stride ? static_cast<size_t>(P) * e_stride : static_cast<size_t>(NE);
+    DeviceBuf d_pot, d_jri, d_e0, d_e1, d_delta, d_raw, d_cnt;
+    if ((rc = d_pot.alloc(static_cast<size_t>(P) * ps * sizeof(double), st))) return rc;
+    if ((rc = d_jri.alloc(static_cast<size_t>(P) * sizeof(int), st))) return rc;
+    if ((rc = d_e0.alloc(n_e * sizeof(double), st))) return rc;
+    if ((rc = d_e1.alloc(n_e * sizeof(double), st))) return rc;
+    if ((rc = d_delta.alloc(static_cast<size_t>(P) * NE * L1 * sizeof(double), st))) return rc;
+    if ((rc = d_raw.alloc(static_cast<size_t>(P) * NE * L1 * 2 * sizeof(double), st))) return rc;
+    if ((rc = d_cnt.alloc(4 * sizeof(unsigned long long), st))) return rc;
+    if (ps != pot_stride) PHSH_CUDA(cudaMemsetAsync(d_pot.p, 0, static_cast<size_t>(P) * ps * sizeof(double), st));
+    PHSH_CUDA(cudaMemcpy2DAsync(d_pot.p, ps * sizeof(double), pot, pot_stride * sizeof(double),
+                                pot_stride * sizeof(double), P, cudaMemcpyHostToDevice, st));
+    PHSH_CUDA(cudaMemcpyAsync(d_jri.p, jri, static_cast<size_t>(P) * sizeof(int), cudaMemcpyHostToDevice, st));
+    PHSH_CUDA(cudaMemcpyAsync(d_e0.p, e_l0, n_e * sizeof(double), cudaMemcpyHostToDevice, st));
+    PHSH_CUDA(cudaMemcpyAsync(d_e1.p, e_l, n_e * sizeof(double), cudaMemcpyHostToDevice, st));
+    PHSH_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(unsigned long long), st));
+    rc = phsh_b200_rel_batch_device(static_cast<double*>(d_pot.p), ps, static_cast<int*>(d_jri.p), P,
+                                    static_cast<double*>(d_e0.p), static_cast<double*>(d_e1.p), e_stride, NE, opts,
+                                    static_cast<double*>(d_delta.p), static_cast<double*>(d_raw.p),
+                                    static_cast<unsigned long long*>(d_cnt.p), st);
+    if (rc) return rc;
+    PHSH_CUDA(cudaMemcpyAsync(delta, d_delta.p, static_cast<size_t>(P) * NE * L1 * sizeof(double),
+                              cudaMemcpyDeviceToHost, st));
+    if (kappa_out)
+        PHSH_CUDA(cudaMemcpyAsync(kappa_out, d_raw.p, static_cast<size_t>(P) * NE * L1 * 2 * sizeof(double),
+                                  cudaMemcpyDeviceToHost, st));
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    PHSH_CUDA(cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    PHSH_CUDA(cudaStreamSynchronize(st));
+    if (counters)
+        for (int i = 0; i < 4; ++i) counters[i] += cnt[i];
+    return 0;
+}
+
+int phsh_b200_conphas_device(const double* phas, int P, int NE, int L, int lmax, double* out, void* stream) {
+    if (P < 0 || NE < 0 || L < 1) {
+        set_error("bad sizes: P=%d NE=%d L=%d", P, NE, L);
+        return PHSH_B200_EINVAL;
+    }
+    if (P == 0 || NE == 0) return 0;
+    int rc = check_current_device();
+    if (rc) return rc;
+    const long warps = static_cast<long>(P) * L;
+    conphas_kernel<<<static_cast<unsigned>((warps + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(phas, P, NE, L,
+                                                                                                        lmax, out);
+    PHSH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int phsh_b200_conphas_host(const double* phas, int P, int NE, int L, int lmax, double* out, int device) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (P <= 0 || NE <= 0 || L < 1) return P < 0 || NE < 0 || L < 1 ? PHSH_B200_EINVAL : 0;
+    cudaStream_t st;
+    PHSH_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard {
+        cudaStream_t s;
+        ~StreamGuard() { cudaStreamDestroy(s); }
+    } guard{st};
+    const size_t bytes = static_cast<size_t>(P) * NE * L * sizeof(double);
+    DeviceBuf a, b;
+    if ((rc = a.alloc(bytes, st))) return rc;
+    if ((rc = b.alloc(bytes, st))) return rc;
+    PHSH_CUDA(cudaMemcpyAsync(a.p, phas, bytes, cudaMemcpyHostToDevice, st));
+    rc = phsh_b200_conphas_device(static_cast<double*>(a.p), P, NE, L, lmax, static_cast<double*>(b.p), st);
+    if (rc) return rc;
+    PHSH_CUDA(cudaMemcpyAsync(out, b.p, bytes, cudaMemcpyDeviceToHost, st));
+    PHSH_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- FP64 peak micro-benchmark: 8 independent register-resident DFMA chains per thread ------------
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, a, b);
+        x1 = __fma_rn(x1, a, b);
+        x2 = __fma_rn(x2, a, b);
+        x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b);
+        x5 = __fma_rn(x5, a, b);
+        x6 = __fma_rn(x6, a, b);
+        x7 = __fma_rn(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+int phsh_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz_est) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    int sms = 0;
+    PHSH_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double* d = nullptr;
+    PHSH_CUDA(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    PHSH_CUDA(cudaEventCreate(&e0));
+    PHSH_CUDA(cudaEventCreate(&e1));
+    const int threads = 256, blocks = sms * 8, iters = 1 << 16;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        PHSH_CUDA(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        PHSH_CUDA(cudaEventRecord(e1));
+        PHSH_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        PHSH_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * iters * static_cast<double>(threads) * blocks;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (tflops) *tflops = best;
+    // 64 DFMA lanes per SM per clock on B200 => clock estimate from the measured rate
+    if (sm_clock_mhz_est) *sm_clock_mhz_est = best * 1e12 / (2.0 * 64.0 * sms) / 1e6;
+    return 0;
+}
+
+}  // extern "C"
+
+#include "phsh_cav_wil_abi.inc"
