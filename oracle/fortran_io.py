@@ -186,3 +186,144 @@ def conphas_file(path: str, lmax: int):
     arr = np.array(data[: n * (lmf + 2)]).reshape(n, lmf + 2)
     energy, phas = arr[:, 0], arr[:, 1:]
     return energy, orc.conphas(phas, lmax)[:, : lmax + 1]
+
+
+# ----------------------------------------------------------------------------- NFORM=0 (cav) and NFORM=1 (wil)
+def efmt(x: float, w: int, d: int) -> str:
+    return dfmt(x, w, d, "E")
+
+
+def write_mufftin_cav(path, atoms):
+    """NFORM=0 mufftin.d as CAVPOT writes it (libphsh.f:2466-2503, formats 217/218/102/219) + the atom count
+    line PHSH_CAV reads first (phsh2.f:123).  atoms: list of dict(name, z, rmt, mtz, rx, v)."""
+    with open(path, "w") as f:
+        f.write("%4d\n" % len(atoms))
+        for a in atoms:
+            f.write(a["name"].ljust(16)[:16] + "\n")
+            f.write(ffmt(a["z"], 8, 4) + ffmt(a["rmt"], 8, 4) + ffmt(a["mtz"], 8, 4) + "\n")
+            f.write("%4d\n" % len(a["rx"]))
+            for r, v in zip(a["rx"], a["v"]):
+                f.write(efmt(r, 14, 5) + efmt(v, 14, 5) + "\n")
+
+
+def read_mufftin_cav(path):
+    with open(path) as f:
+        lines = f.readlines()
+    n = iread(_pad(lines[0], 4)[:4])
+    i, atoms = 1, []
+    for _ in range(n):
+        name = _pad(lines[i], 16)[:16]
+        h = _pad(lines[i + 1], 24)
+        z, rmt, mtz = fread(h[0:8], 4), fread(h[8:16], 4), fread(h[16:24], 4)
+        ntab = iread(_pad(lines[i + 2], 4)[:4])
+        rx, v = [], []
+        for r in range(ntab):
+            ln = _pad(lines[i + 3 + r], 28)
+            rx.append(f32(fread(ln[0:14], 5)))
+            v.append(f32(fread(ln[14:28], 5)))
+        atoms.append(dict(name=name, z=z, rmt=f32(rmt), mtz=mtz, rx=np.array(rx), v=np.array(v)))
+        i += 3 + ntab
+    return atoms
+
+
+def phsh_cav_file(mufftin, phasout, dataph, zph, real32=False, asbuilt=False, conphas_header=False):
+    """PHSH_CAV as a whole (phsh2.f:99-174; as-built routing of the rows to DATAPH: libphsh.f:3634-3646)."""
+    atoms = read_mufftin_cav(mufftin)
+    e_ha = orc.cav_energy_grid(1.0, 12.0, 0.25, real32=True)
+    NL = 12
+    ianz = int(np.float32((12.0 - 1.0) / 0.25 + 1.01))
+    res = []
+    with open(phasout, "w") as fp, open(dataph, "w") as fd, open(zph, "w") as fz:
+        rows = fd if asbuilt else fp
+        fd.write("TitleText: DELTA(E)\n")
+        for a in atoms:
+            n = len(a["rx"])
+            phs, rc = orc.cav_batch(a["v"][None], a["rx"][None], [n], [a["rmt"]], 2.0 * e_ha, NL=NL, real32=real32,
+                                    asbuilt=asbuilt)
+            phs = phs[0]
+            res.append(phs)
+            fz.write("PHASE SHIFTS FOR " + a["name"] + "  ATOMIC NUMBER," + ffmt(a["z"], 6, 1) + "\n")
+            fz.write("MUFFIN-TIN RADIUS" + ffmt(a["rmt"], 8, 4) + "       MUFFIN-TIN ZERO LEVEL" + ffmt(a["mtz"] / 2.0, 8, 4) +
+                     " HARTREES\n")
+            rows.write("NON-RELATIVISTIC PHASE SHIFTS FOR " + a["name"][0:4] + a["name"][8:12] + "\n")
+            rows.write(ffmt(1.0, 9, 4) + ffmt(0.25, 9, 4) + "  %3d  %3d\n" % (ianz, NL - 1 if conphas_header else NL))
+            for ie, e in enumerate(e_ha):
+                fz.write("ENERGY" + ffmt(e, 8, 4) + " HARTREES\n")
+                zl = ""
+                for l in range(NL):
+                    zl += ffmt(phs[ie, l], 12, 5)
+                    if l % 10 == 9 or l == NL - 1:
+                        zl += "\n"
+                fz.write(zl)
+                items = [float(np.float32(e) * np.float32(27.21))] + list(phs[ie])
+                for k in range(0, len(items), 9):
+                    rec = items[k:k + 9]
+                    rows.write(ffmt(rec[0], 9, 4) + "".join(ffmt(v, 8, 4) for v in rec[1:]) + "\n")
+            for kk in range(NL):
+                fd.write('"L=%2d\n' % kk)
+                for ie, e in enumerate(e_ha):
+                    fd.write(list_directed_real(e, 8) + list_directed_real(phs[ie, kk], 8) + "\n")
+                fd.write("\n")
+    return res
+
+
+def write_mufftin_wil(path, atoms):
+    """NFORM=1 mufftin.d as CAVPOT writes it (libphsh.f:2443, 2470, 2493-2497, formats 220/221/219)."""
+    with open(path, "w") as f:
+        f.write(" &NL2 NRR=%2d &end\n" % len(atoms))
+        for a in atoms:
+            f.write(" &NL16 Z=" + ffmt(a["z"], 7, 4) + ",RT=" + ffmt(a["rt"], 7, 4) + " &end\n")
+            for r, rv in zip(a["r"], a["rv"]):
+                f.write(efmt(r, 14, 5) + efmt(rv, 14, 5) + "\n")
+            f.write(efmt(-1.0, 14, 5) + "\n")
+
+
+def read_mufftin_wil(path):
+    import re
+    with open(path) as f:
+        lines = f.readlines()
+    nrr = int(re.search(r"NRR\s*=\s*(\d+)", lines[0]).group(1))
+    i, atoms = 1, []
+    for _ in range(nrr):
+        m = re.search(r"Z\s*=\s*([-0-9.]+)\s*,\s*RT\s*=\s*([-0-9.]+)", lines[i])
+        z, rt = f32(float(m.group(1))), f32(float(m.group(2)))
+        i += 1
+        rs, zs = [], []
+        for _r in range(200):
+            ln = _pad(lines[i], 28)
+            i += 1
+            rs.append(f32(fread(ln[0:14], 5)))
+            zs.append(f32(fread(ln[14:28], 5)))
+            if rs[-1] < 0:
+                break
+        atoms.append(dict(z=z, rt=rt, rs=np.array(rs), zs=np.array(zs)))
+    return atoms
+
+
+def phsh_wil_file(mufftin, phasout, dataph, zph, real32=False):
+    """PHSH_WIL as a whole (phsh2.f:314-433) with the namelist defaults E1=4, E2=24, NE=30, NL=9, NR=101, NEUO=2."""
+    atoms = read_mufftin_wil(mufftin)
+    NE, NL, NR = 30, 9, 101
+    e = orc.wil_energy_grid(4.0, 24.0, NE, real32=True)
+    eo = np.array([float(np.float32(0.5) * np.float32(x)) for x in e])
+    dels = []
+    for a in atoms:
+        r = orc.wil_batch(a["rs"][None], a["zs"][None], [len(a["rs"])], [a["z"]], [a["rt"]], e, NL=NL, NR=NR,
+                          real32=real32)
+        dels.append(r["del"][0])
+    with open(phasout, "w") as fp, open(dataph, "w") as fd, open(zph, "w") as fz:
+        fz.write("&NL2\n IP=1,\n NRR=%d,\n /\n" % len(atoms))
+        fd.write("TitleText: DELTA(E)\n")
+        for d in dels:
+            for kk in range(NL):
+                fd.write('"L=%2d\n' % kk)
+                for ie in range(NE):
+                    fd.write(list_directed_real(eo[ie], 4) + list_directed_real(f32(d[ie, kk]), 4) + "\n")
+                fd.write("\n")
+        fp.write(" BE CAREFUL ABOUT THE ORDER OF THE ELEMENTS\n")
+        for ie in range(NE):
+            fp.write(ffmt(eo[ie], 7, 4) + "\n")
+            for d in dels:
+                for k in range(0, NL, 10):
+                    fp.write("".join(ffmt(v, 7, 4) for v in d[ie, k:k + 10]) + "\n")
+    return dels

@@ -42,6 +42,9 @@ _SIGNATURES = {
     "phsh_b200_device_count": (C.c_int, []),
     "phsh_b200_rel_batch_device": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_long, C.c_int,
                                              C.POINTER(RelOpts), _dp, _dp, _dp, C.c_void_p]),
+    "phsh_b200_rel_integrate_device": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_long, C.c_int,
+                                                 C.POINTER(RelOpts), _dp, _dp, C.c_void_p]),
+    "phsh_b200_rel_energy_axis_device": (C.c_int, [_dp, C.c_int, C.c_int, C.POINTER(RelOpts), _dp, C.c_void_p]),
     "phsh_b200_rel_batch_host": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_long, C.c_int,
                                            C.POINTER(RelOpts), _dp, _dp, _dp, C.c_int]),
     "phsh_b200_conphas_device": (C.c_int, [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_void_p]),

@@ -202,3 +202,104 @@ def fp64_peak(device=0):
     tf, mhz = C.c_double(), C.c_double()
     _lib.check(lib.phsh_b200_fp64_peak(int(device), C.byref(tf), C.byref(mhz)))
     return tf.value, mhz.value
+
+
+def phsh_cav_batch(V, RX, ntab, rmt, e_ryd, NL=12, *, unwrap=False, asbuilt=False, device=0):
+    """Non-relativistic CAVLEED phase shifts (PS, libphsh.f:3704-3803).
+
+    V, RX  [P, S]  V(r) in Rydberg and r on the Loucks grid r_i = exp(-8.8 + 0.05 (i-1)); ntab [P] valid points
+    rmt    [P]     matching radius; e_ryd [NE] energies in Rydberg.  Returns phs [P, NE, NL].
+    """
+    lib = _lib.load()
+    flags = _flags(unwrap=unwrap, asbuilt=asbuilt)
+    if _is_cuda_tensor(V):
+        import torch
+        dev = V.device
+        V = V.contiguous()
+        RX = torch.as_tensor(RX, dtype=torch.float64, device=dev).contiguous()
+        P, S = V.shape
+        if S % 2:
+            V = torch.nn.functional.pad(V, (0, 1)).contiguous()
+            RX = torch.nn.functional.pad(RX, (0, 1)).contiguous()
+            S += 1
+        nt = torch.as_tensor(ntab, dtype=torch.int32, device=dev).expand(P).contiguous()
+        rm = torch.as_tensor(rmt, dtype=torch.float64, device=dev).expand(P).contiguous()
+        e = torch.as_tensor(e_ryd, dtype=torch.float64, device=dev).contiguous()
+        out = torch.empty((P, e.shape[0], NL), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.phsh_b200_cav_batch_device(_ptr(V), _ptr(RX), S, _ptr(nt), _ptr(rm), P, _ptr(e), e.shape[0],
+                                                      int(NL), flags, _ptr(out),
+                                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return out
+    V, RX = _np64(V), _np64(RX)
+    P, S = V.shape
+    nt = _np32i(ntab, P)
+    rm = np.ascontiguousarray(np.broadcast_to(_np64(rmt), (P,)))
+    e = _np64(e_ryd)
+    out = np.empty((P, e.shape[0], NL))
+    _lib.check(lib.phsh_b200_cav_batch_host(_ptr(V), _ptr(RX), S, _ptr(nt), _ptr(rm), P, _ptr(e), e.shape[0], int(NL),
+                                            flags, _ptr(out), int(device)))
+    return out
+
+
+def phsh_wil_batch(rs, zs, nrows, Z, RT, e, NL=9, NR=101, *, unwrap=False, device=0):
+    """Williams phase shifts (PHSH_WIL, libphsh.f:3893-4062) incl. its 0.7-rad / pi continuity pass.
+
+    rs, zs [P, S]  rows (r, r*V) as in the NFORM=1 file (terminated by a row with r<0), nrows [P]
+    Z, RT  [P]     atomic number and muffin-tin radius; e [NE] energies in Rydberg.  Returns del [P, NE, NL].
+    """
+    lib = _lib.load()
+    flags = _flags(unwrap=unwrap)
+    if _is_cuda_tensor(rs):
+        import torch
+        dev = rs.device
+        rs = rs.contiguous()
+        zs = torch.as_tensor(zs, dtype=torch.float64, device=dev).contiguous()
+        P, S = rs.shape
+        if S % 2:
+            rs = torch.nn.functional.pad(rs, (0, 1)).contiguous()
+            zs = torch.nn.functional.pad(zs, (0, 1)).contiguous()
+            S += 1
+        nr = torch.as_tensor(nrows, dtype=torch.int32, device=dev).expand(P).contiguous()
+        z = torch.as_tensor(Z, dtype=torch.float64, device=dev).expand(P).contiguous()
+        rt = torch.as_tensor(RT, dtype=torch.float64, device=dev).expand(P).contiguous()
+        ee = torch.as_tensor(e, dtype=torch.float64, device=dev).contiguous()
+        out = torch.empty((P, ee.shape[0], NL), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.phsh_b200_wil_batch_device(_ptr(rs), _ptr(zs), S, _ptr(nr), _ptr(z), _ptr(rt), P, _ptr(ee),
+                                                      ee.shape[0], int(NL), int(NR), flags, _ptr(out),
+                                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return out
+    rs, zs = _np64(rs), _np64(zs)
+    P, S = rs.shape
+    nr = _np32i(nrows, P)
+    z = np.ascontiguousarray(np.broadcast_to(_np64(Z), (P,)))
+    rt = np.ascontiguousarray(np.broadcast_to(_np64(RT), (P,)))
+    ee = _np64(e)
+    out = np.empty((P, ee.shape[0], NL))
+    _lib.check(lib.phsh_b200_wil_batch_host(_ptr(rs), _ptr(zs), S, _ptr(nr), _ptr(z), _ptr(rt), P, _ptr(ee),
+                                            ee.shape[0], int(NL), int(NR), flags, _ptr(out), int(device)))
+    return out
+
+
+def _file_call(fn, a, b, c, d, flags, max_energies, max_jri, device):
+    opts = _lib.FileOpts(int(flags), int(max_energies), int(max_jri), int(device))
+    _lib.check(fn(str(a).encode(), str(b).encode(), str(c).encode(), str(d).encode(), C.byref(opts)))
+
+
+def phsh_rel_file(mufftin, phasout, dataph, inpdat, *, asbuilt=False, real32=False, fast=False, max_energies=250,
+                  max_jri=340, device=0):
+    """``libphsh.phsh_rel(mufftin, phasout, dataph, inpdat)`` (libphsh.f:4552) on the GPU."""
+    _file_call(_lib.load().phsh_b200_rel_file, mufftin, phasout, dataph, inpdat,
+               _flags(asbuilt=asbuilt, real32=real32, fast=fast), max_energies, max_jri, device)
+
+
+def phsh_cav_file(mufftin, phasout, dataph, zph, *, asbuilt=False, conphas_header=False, device=0):
+    """``libphsh.phsh_cav(mufftin, phasout, dataph, zph)`` (libphsh.f:3585; original layout phsh2.f:99-174)."""
+    _file_call(_lib.load().phsh_b200_cav_file, mufftin, phasout, dataph, zph,
+               _flags(asbuilt=asbuilt) | (0x20 if conphas_header else 0), 250, 340, device)
+
+
+def phsh_wil_file(mufftin, phasout, dataph, zph, *, device=0):
+    """``libphsh.phsh_wil(mufftin, phasout, dataph, zph)`` (libphsh.f:3893; original control flow phsh2.f:314-433)."""
+    _file_call(_lib.load().phsh_b200_wil_file, mufftin, phasout, dataph, zph, 0, 250, 340, device)

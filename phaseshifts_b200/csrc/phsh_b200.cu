@@ -39,6 +39,15 @@ int check_current_device() {
         set_error("device %d has compute capability %d.x; this library is built for sm_100a (B200) only", dev, major);
         return PHSH_B200_ENODEV;
     }
+    static std::once_flag pool_once[64];
+    if (dev < 64)
+        std::call_once(pool_once[dev], [dev]() {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long thr = ~0ull;  // keep stream-ordered scratch cached between calls
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+        });
     return 0;
 }
 
@@ -56,15 +65,6 @@ int select_device(int device) {
         return PHSH_B200_EINVAL;
     }
     PHSH_CUDA(cudaSetDevice(device));
-    static std::once_flag pool_once[64];
-    if (device < 64)
-        std::call_once(pool_once[device], [device]() {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-                unsigned long long thr = ~0ull;  // keep scratch cached between calls
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            }
-        });
     return check_current_device();
 }
 
@@ -103,9 +103,9 @@ static RelConsts make_rel_consts(const phsh_b200_rel_opts& o) {
 }
 
 template <bool FAST, class Real>
-static int launch_rel(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0, const double* e_l,
-                      long e_stride, int NE, const RelConsts& c, int jpad, double* raw, double* delta,
-                      unsigned long long* counters, cudaStream_t st) {
+static int launch_rel_integrate(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0,
+                                const double* e_l, long e_stride, int NE, const RelConsts& c, int jpad, double* raw,
+                                unsigned long long* counters, cudaStream_t st) {
     const int L1 = c.lsm + 1;
     int block = NE >= 128 ? 128 : ((NE + 31) / 32) * 32;
     const int chunks = (NE + block - 1) / block;
@@ -120,9 +120,15 @@ static int launch_rel(const double* pot, long pot_stride, const int* jri, int P,
     kern<<<static_cast<unsigned>(grid), block, smem, st>>>(pot, pot_stride, jri, e_l0, e_l, e_stride, NE, c, lgroups,
                                                             chunks, jpad, raw, counters);
     PHSH_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <class Real>
+static int launch_rel_energy_axis(const double* raw, int P, int NE, int lsm, int flags, double* delta, cudaStream_t st) {
+    const int L1 = lsm + 1;
     const long warps = static_cast<long>(P) * L1;
     rel_energy_axis_kernel<Real><<<static_cast<unsigned>((warps + 3) / 4), 128, 0, st>>>(
-        raw, P, L1, NE, (c.flags & PHSH_B200_UNWRAP) ? 1 : 0, delta);
+        raw, P, L1, NE, (flags & PHSH_B200_UNWRAP) ? 1 : 0, delta);
     PHSH_CUDA(cudaGetLastError());
     return 0;
 }
@@ -165,13 +171,17 @@ int phsh_b200_device_count(void) {
     return n;
 }
 
-int phsh_b200_rel_batch_device(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0,
-                               const double* e_l, long e_stride, int NE, const phsh_b200_rel_opts* opts, double* delta,
-                               double* kappa_out, unsigned long long* counters, void* stream) {
+int phsh_b200_rel_integrate_device(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0,
+                                   const double* e_l, long e_stride, int NE, const phsh_b200_rel_opts* opts,
+                                   double* raw, unsigned long long* counters, void* stream) {
     int rc = rel_check(pot_stride, P, NE, opts);
     if (rc) return rc;
     if ((reinterpret_cast<uintptr_t>(pot) & 15) || (pot_stride & 1)) {
         set_error("pot must be 16-byte aligned with an even pot_stride (TMA bulk copy)");
+        return PHSH_B200_EINVAL;
+    }
+    if ((reinterpret_cast<uintptr_t>(raw) & 15)) {
+        set_error("raw must be 16-byte aligned");
         return PHSH_B200_EINVAL;
     }
     if (P == 0 || NE == 0) return 0;
@@ -180,6 +190,38 @@ int phsh_b200_rel_batch_device(const double* pot, long pot_stride, const int* jr
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!e_l) e_l = e_l0;
     const RelConsts c = make_rel_consts(*opts);
+    const int jpad = static_cast<int>((pot_stride + 1) & ~1L);
+    const bool fast = (opts->flags & PHSH_B200_FAST) != 0, r32 = (opts->flags & PHSH_B200_REAL32) != 0;
+    if (fast && r32)
+        return launch_rel_integrate<true, float>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, counters, st);
+    if (fast)
+        return launch_rel_integrate<true, double>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, counters, st);
+    if (r32)
+        return launch_rel_integrate<false, float>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, counters, st);
+    return launch_rel_integrate<false, double>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, counters, st);
+}
+
+int phsh_b200_rel_energy_axis_device(const double* raw, int P, int NE, const phsh_b200_rel_opts* opts, double* delta,
+                                     void* stream) {
+    if (!opts || P < 0 || NE < 0 || opts->lsm < 0) {
+        set_error("bad arguments");
+        return PHSH_B200_EINVAL;
+    }
+    if (P == 0 || NE == 0) return 0;
+    int rc = check_current_device();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (opts->flags & PHSH_B200_REAL32) return launch_rel_energy_axis<float>(raw, P, NE, opts->lsm, opts->flags, delta, st);
+    return launch_rel_energy_axis<double>(raw, P, NE, opts->lsm, opts->flags, delta, st);
+}
+
+int phsh_b200_rel_batch_device(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0,
+                               const double* e_l, long e_stride, int NE, const phsh_b200_rel_opts* opts, double* delta,
+                               double* kappa_out, unsigned long long* counters, void* stream) {
+    int rc = rel_check(pot_stride, P, NE, opts);
+    if (rc) return rc;
+    if (P == 0 || NE == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int L1 = opts->lsm + 1;
     DeviceBuf scratch;
     double* raw = kappa_out;
@@ -188,15 +230,9 @@ int phsh_b200_rel_batch_device(const double* pot, long pot_stride, const int* jr
         if (rc) return rc;
         raw = static_cast<double*>(scratch.p);
     }
-    const int jpad = static_cast<int>((pot_stride + 1) & ~1L);
-    const bool fast = (opts->flags & PHSH_B200_FAST) != 0, r32 = (opts->flags & PHSH_B200_REAL32) != 0;
-    if (fast && r32)
-        return launch_rel<true, float>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, delta, counters, st);
-    if (fast)
-        return launch_rel<true, double>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, delta, counters, st);
-    if (r32)
-        return launch_rel<false, float>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, delta, counters, st);
-    return launch_rel<false, double>(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, c, jpad, raw, delta, counters, st);
+    rc = phsh_b200_rel_integrate_device(pot, pot_stride, jri, P, e_l0, e_l, e_stride, NE, opts, raw, counters, stream);
+    if (rc) return rc;
+    return phsh_b200_rel_energy_axis_device(raw, P, NE, opts, delta, stream);
 }
 
 int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri, int P, const double* e_l0,
