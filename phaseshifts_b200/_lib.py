@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libphsh_b200.so")
+LIB_PATH = os.environ.get("PHSH_B200_LIB") or os.path.join(_PKG, "libphsh_b200.so")
 
 OK, EINVAL, ENODEV, ECUDA, EIO, ENOMEM = 0, -1, -2, -3, -4, -5
 ASBUILT, UNWRAP, FAST, REAL32, NONREL = 0x1, 0x2, 0x4, 0x8, 0x10

@@ -1,6 +1,7 @@
 // phsh_b200.cu -- C-ABI entry points (include/phsh_b200.h) and launch logic for the sm_100a kernels.
 // There is deliberately no CPU implementation here: without a CUDA device every compute call fails.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -114,7 +115,9 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
     const long target = 148L * 8;
     while (static_cast<long>(P) * chunks * lgroups < target && lgroups < L1) ++lgroups;
     const size_t smem = static_cast<size_t>(2 * jpad) * sizeof(double) + 16;
-    auto kern = rel_integrate_kernel<FAST, Real>;
+    static const int minb = getenv("PHSH_B200_MINB") ? atoi(getenv("PHSH_B200_MINB")) : 4;
+    auto kern = minb == 5 ? rel_integrate_kernel<FAST, Real, 5> : minb == 6 ? rel_integrate_kernel<FAST, Real, 6>
+                                                                              : rel_integrate_kernel<FAST, Real, 4>;
     if (smem > 48 * 1024) PHSH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long grid = static_cast<long>(P) * lgroups * chunks;
     kern<<<static_cast<unsigned>(grid), block, smem, st>>>(pot, pot_stride, jri, e_l0, e_l, e_stride, NE, c, lgroups,

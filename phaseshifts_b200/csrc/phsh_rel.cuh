@@ -73,6 +73,26 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 
+// Convergence test of the corrector (libphsh.f:4868-4870): iterate again if the U test fails or the W test
+// fails.  `||` short-circuits into a real branch, so the W test only runs on warps where some lane passed
+// the U test.  Measured alternatives that were slower on B200 and are not kept: magnitude compares on the
+// integer pipe (LOP3+ISETP instead of DSETP: +11 % time) and a warp-vote guarded W test (+25 %).
+__device__ __forceinline__ bool milne_again(double cu, double pu, double cw, double pw) {
+    const double TEST = 1.0e6;
+    return (fabs(dmul(TEST, dsub(cu, pu))) > fabs(cu)) || !(fabs(dmul(TEST, dsub(cw, pw))) <= fabs(cw));
+}
+
+// Tuning knob: the corrector loop (at most 6 evaluations) is fully unrolled by default (fastest measured);
+// -DPHSH_CORR_UNROLL=0 keeps it rolled.
+#ifndef PHSH_CORR_UNROLL
+#define PHSH_CORR_UNROLL 1
+#endif
+#if PHSH_CORR_UNROLL == 0
+#define PHSH_CORR_PRAGMA _Pragma("unroll 1")
+#else
+#define PHSH_CORR_PRAGMA
+#endif
+
 // One Milne step N -> N+1 on the rotating window.  Slot (PH+k)%6 holds index N-5+k.
 //   predictor  libphsh.f:4855-4858, corrector + test :4860-4877.
 // su/sw carry UP(N-2)+UP(N) of the previous step == UP(NM1)+UP(NM3) of this one (IEEE add commutes).
@@ -83,7 +103,7 @@ __device__ __forceinline__ void milne_step(double (&u)[6], double (&w)[6], doubl
     constexpr int i5 = PH, i4 = (PH + 1) % 6, i3 = (PH + 2) % 6, i2 = (PH + 3) % 6, i1 = (PH + 4) % 6,
                   i0 = (PH + 5) % 6;
     (void)i4;
-    const double T7 = 7.0, T11 = 11.0, T12 = 12.0, T14 = 14.0, T26 = 26.0, T32 = 32.0, TEST = 1.0e6;
+    const double T7 = 7.0, T11 = 11.0, T12 = 12.0, T14 = 14.0, T26 = 26.0, T32 = 32.0;
     double TC, VCT, pu, pw, cu, cw, up1, wp1;
     if (!FAST) {
         TC = dadd(dmul(EV, T), POTN);
@@ -96,6 +116,7 @@ __device__ __forceinline__ void milne_step(double (&u)[6], double (&w)[6], doubl
         const double Cu = dmul(T12, up[i1]);
         const double Cw = dmul(T12, wp[i1]);
         int nit = 0;
+        PHSH_CORR_PRAGMA
         for (;;) {
             up1 = dsub(dmul(VCT, pw), dmul(XK, pu));
             wp1 = dsub(dmul(XK, pw), dmul(TC, pu));
@@ -103,9 +124,8 @@ __device__ __forceinline__ void milne_step(double (&u)[6], double (&w)[6], doubl
             cu = dadd(u[i3], dmul(dadd(__fma_rn(T32, su, dmul(T7, dadd(up1, up[i3]))), Cu), c.XMFT));
             cw = dadd(w[i3], dmul(dadd(__fma_rn(T32, sw, dmul(T7, dadd(wp1, wp[i3]))), Cw), c.XMFT));
             ++evals;
-            const bool again =
-                (fabs(dmul(TEST, dsub(cu, pu))) > fabs(cu)) || !(fabs(dmul(TEST, dsub(cw, pw))) <= fabs(cw));
-            if (!again || nit >= 5) break;
+            if (nit >= 5) break;  // sixth evaluation is accepted whatever the test says (libphsh.f:4870-4871)
+            if (!milne_again(cu, pu, cw, pw)) break;
             ++nit;
             pu = cu;
             pw = cw;
@@ -121,14 +141,15 @@ __device__ __forceinline__ void milne_step(double (&u)[6], double (&w)[6], doubl
         const double Iu = __fma_rn(T32, su, T12 * up[i1]);
         const double Iw = __fma_rn(T32, sw, T12 * wp[i1]);
         int nit = 0;
+        PHSH_CORR_PRAGMA
         for (;;) {
             up1 = __fma_rn(VCT, pw, -(XK * pu));
             wp1 = __fma_rn(XK, pw, -(TC * pu));
             cu = __fma_rn(c.XMFT, __fma_rn(T7, up1 + up[i3], Iu), u[i3]);
             cw = __fma_rn(c.XMFT, __fma_rn(T7, wp1 + wp[i3], Iw), w[i3]);
             ++evals;
-            const bool again = (fabs(TEST * (cu - pu)) > fabs(cu)) || !(fabs(TEST * (cw - pw)) <= fabs(cw));
-            if (!again || nit >= 5) break;
+            if (nit >= 5) break;  // sixth evaluation is accepted whatever the test says (libphsh.f:4870-4871)
+            if (!milne_again(cu, pu, cw, pw)) break;
             ++nit;
             pu = cu;
             pw = cw;
@@ -301,8 +322,8 @@ __device__ __forceinline__ Real sbfit_match(const Bessel<Real>& b, double T, int
 // kernel A: integrate + match.  raw[((p*L1 + l)*NE + ie)*2 + {0: JFD (kappa=l), 1: JFU (kappa=-l-1)}]
 // grid.x = P * lgroups * chunks (p major), block = 32..128 threads, dyn smem = 2*jpad doubles + 16 B
 // =================================================================================================
-template <bool FAST, class Real>
-__global__ void __launch_bounds__(128)
+template <bool FAST, class Real, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     rel_integrate_kernel(const double* __restrict__ pot, long pot_stride, const int* __restrict__ jri_arr,
                          const double* __restrict__ e_l0, const double* __restrict__ e_l, long e_stride, int NE,
                          const __grid_constant__ RelConsts c, int lgroups, int chunks, int jpad,
@@ -353,16 +374,22 @@ __global__ void __launch_bounds__(128)
 
     for (int l = l_hi; l >= l_lo; --l) {
         const double E = (l == 0) ? E0 : E1;
-        const double dlu = dlgkap_dev<FAST>(pot_s, r_s, jri, E, -(l + 1), c, steps, evals) / c4pi;
-        ++calls;
+        // kappa = -(l+1) first, then kappa = l.  One copy of the integrator in the instruction stream: with two
+        // inlined copies the unrolled Milne phases overflow the instruction cache (measured 287 vs 220 ms).
+        double dlu = 0.0, dld = 0.0;
+        const int nk = l > 0 ? 2 : 1;
+#pragma unroll 1
+        for (int s = 0; s < nk; ++s) {
+            const double v = dlgkap_dev<FAST>(pot_s, r_s, jri, E, s == 0 ? -(l + 1) : l, c, steps, evals) / c4pi;
+            ++calls;
+            if (s == 0)
+                dlu = v;
+            else
+                dld = v;
+        }
         const Bessel<Real> b = sbfit_bessel<Real>(E, R, l, asbuilt);
         const Real JFU = sbfit_match<Real>(b, dlu, l);
-        Real JFD = JFU;
-        if (l > 0) {
-            const double dld = dlgkap_dev<FAST>(pot_s, r_s, jri, E, l, c, steps, evals) / c4pi;
-            ++calls;
-            JFD = sbfit_match<Real>(b, dld, l);
-        }
+        const Real JFD = l > 0 ? sbfit_match<Real>(b, dld, l) : JFU;
         if (active) {
             double2 o;
             o.x = static_cast<double>(JFD);

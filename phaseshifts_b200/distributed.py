@@ -1,0 +1,89 @@
+"""Multi-GPU sharding of a sweep: one process per GPU, ``torch.distributed`` for the plumbing only.
+
+Every (potential, l, kappa) integration is independent and the only coupling runs along the energy axis
+of one (potential, l) (LVOR average, conphas), so the sweep is partitioned by potential index: rank r of
+W owns the contiguous block ``shard_range(P, r, W)`` and there is NO data-path collective.  The optional
+gather at the end (``all_gather`` of equally padded blocks; NCCL over NVLink for device tensors, gloo for
+host tensors) only serves a consumer that wants the whole array in one place.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def shard_range(P: int, rank: int, world: int):
+    """Contiguous block partition of ``range(P)``; the first ``P % world`` ranks get one extra item."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank/world: %r/%r" % (rank, world))
+    base, extra = divmod(int(P), world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def rank_world():
+    d = _dist()
+    if d is not None:
+        return d.get_rank(), d.get_world_size()
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def gather_blocks(local, P: int, group=None):
+    """All-gather the per-rank blocks ``local`` [P_r, ...] (torch tensor, cpu or cuda) into [P, ...] on every rank."""
+    import torch
+    d = _dist()
+    if d is None:
+        return local
+    rank, world = d.get_rank(group), d.get_world_size(group)
+    sizes = [shard_range(P, r, world)[1] - shard_range(P, r, world)[0] for r in range(world)]
+    if local.shape[0] != sizes[rank]:
+        raise ValueError("rank %d holds %d rows, expected %d" % (rank, local.shape[0], sizes[rank]))
+    pad = max(sizes)
+    buf = local.new_zeros((pad,) + tuple(local.shape[1:]))
+    buf[: local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    d.all_gather(parts, buf, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+def phsh_rel_sweep(pot, jri, energies_ryd, lmax, *, gather=True, compute=None, group=None, **kwargs):
+    """Relativistic phase shifts of ``pot`` [P, J] sharded over the ranks of the current process group.
+
+    Each rank computes ``shard_range(P, rank, world)`` on its own GPU (``LOCAL_RANK``) through
+    ``api.phsh_rel_batch`` (or ``compute``, same signature -- the CPU tests inject the oracle there) and, if
+    ``gather``, every rank returns the full [P, NE, lmax+1] array; otherwise ``(local_block, (start, stop))``.
+    """
+    import torch
+    rank, world = rank_world()
+    pot = np.asarray(pot)
+    P = pot.shape[0]
+    jri = np.broadcast_to(np.asarray(jri, dtype=np.int32), (P,))
+    a, b = shard_range(P, rank, world)
+    e = np.asarray(energies_ryd)
+    e_loc = e[a:b] if e.ndim == 2 else e
+    if "energies_l0" in kwargs and kwargs["energies_l0"] is not None and np.asarray(kwargs["energies_l0"]).ndim == 2:
+        kwargs = dict(kwargs, energies_l0=np.asarray(kwargs["energies_l0"])[a:b])
+    if compute is None:
+        from . import api
+        local_rank = int(os.environ.get("LOCAL_RANK", rank))
+
+        def compute(p_, j_, e_, l_, **kw):
+            return api.phsh_rel_batch(p_, j_, e_, l_, device=local_rank, **kw)
+    NE = e.shape[-1]
+    if b > a:
+        local = np.asarray(compute(pot[a:b], jri[a:b], e_loc, lmax, **kwargs))
+    else:
+        local = np.empty((0, NE, lmax + 1))
+    if not gather or world == 1:
+        return local if world == 1 and gather else (local, (a, b))
+    t = torch.from_numpy(np.ascontiguousarray(local))
+    d = _dist()
+    if d is not None and d.get_backend(group) == "nccl":
+        t = t.cuda(int(os.environ.get("LOCAL_RANK", rank)))
+    return gather_blocks(t, P, group=group).cpu().numpy()

@@ -1,0 +1,139 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol declared in
+include/phsh_b200.h, refuses to compute without a GPU (no CPU fallback), and the host-side bookkeeping
+(energy grids, workloads, option plumbing) is right.  No compute calls on a GPU here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from phaseshifts_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "phsh_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(phsh_b200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from phaseshifts_b200 import _lib
+    decl = _declared_symbols()
+    assert len(decl) >= 17
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in decl:
+        assert hasattr(raw, name), name
+    assert sorted(_lib.EXPORTED_SYMBOLS) == decl  # the ctypes table binds exactly what the header declares
+
+
+def test_header_cites_reference_interfaces():
+    txt = open(os.path.join(ROOT, "include", "phsh_b200.h")).read()
+    for needle in ("libphsh.f:4552", "libphsh.f:3585", "libphsh.f:3893", "conphas.py:437-456", "phsh.py:338"):
+        assert needle in txt
+
+
+def test_version_and_error_channel(lib):
+    assert b"sm_100a" in lib.phsh_b200_version()
+    assert isinstance(lib.phsh_b200_last_error(), bytes)
+
+
+def test_no_cpu_fallback(lib, tmp_path):
+    """Without a CUDA device every compute entry point must fail loudly (ENODEV), never compute on the host."""
+    from phaseshifts_b200 import api, _lib, PhshB200Error
+    if lib.phsh_b200_device_count() > 0:
+        pytest.skip("a GPU is visible; the no-device path cannot be exercised here")
+    pot = np.ones((1, 340))
+    with pytest.raises(PhshB200Error) as e:
+        api.phsh_rel_batch(pot, [321], np.array([1.0, 2.0]), 3)
+    assert e.value.code == _lib.ENODEV and "no CPU fallback" in str(e.value)
+    with pytest.raises(PhshB200Error):
+        api.conphas(np.zeros((4, 3)))
+    with pytest.raises(PhshB200Error):
+        api.phsh_cav_batch(np.ones((1, 250)), np.ones((1, 250)), [250], [2.0], np.array([1.0]))
+    with pytest.raises(PhshB200Error):
+        api.phsh_wil_batch(np.ones((1, 202)), np.ones((1, 202)), [100], [10.0], [2.0], np.array([1.0]))
+    muff = os.path.join(ROOT, "tests", "golden", "Re0001", "mufftin_Re_slab.d")
+    with pytest.raises(PhshB200Error) as e:
+        api.phsh_rel_file(muff, str(tmp_path / "a"), str(tmp_path / "b"), str(tmp_path / "c"))
+    assert e.value.code == _lib.ENODEV
+
+
+def test_argument_validation_happens_before_device_selection(lib, tmp_path):
+    from phaseshifts_b200 import api, _lib, PhshB200Error
+    with pytest.raises(PhshB200Error) as e:
+        api.phsh_rel_batch(np.ones((1, 340)), [400], np.array([1.0]), 3)  # jri > J
+    assert e.value.code == _lib.EINVAL
+    with pytest.raises(PhshB200Error) as e:
+        api.phsh_rel_batch(np.ones((1, 340)), [321], np.array([1.0]), 3, dx=-1.0)
+    assert e.value.code == _lib.EINVAL
+    with pytest.raises(PhshB200Error) as e:
+        api.phsh_rel_file(str(tmp_path / "missing.d"), "a", "b", "c")
+    assert e.value.code == _lib.EIO
+
+
+def test_missing_library_raises(monkeypatch, tmp_path):
+    from phaseshifts_b200 import _lib
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.PhshB200Error) as e:
+        _lib.load()
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_energy_grid_equals_oracle(oracle):
+    from phaseshifts_b200 import api
+    for (es, de, ue, cap, asb) in [(20, 5, 300, 250, False), (20, 5, 600, 250, False), (20, 1, 1019, 0, False),
+                                   (20, 1, 600, 250, False), (20, 5, 300, 250, True), (10, 0, 5, 250, False),
+                                   (0.5, 0.37, 77.7, 0, True)]:
+        a = api.rel_energy_grid(es, de, ue, max_energies=cap, asbuilt=asb)
+        b = oracle.rel_energy_grid(es, de, ue, ncap=cap, asbuilt=asb)
+        assert a["n_header"] == b["n_header"]
+        for k in ("e_l0", "e_l", "e_ev"):
+            assert np.array_equal(a[k], b[k]), (k, es, de, ue)
+    g = api.rel_energy_grid(20, 1, 600)
+    assert g["n_header"] == 581 and len(g["e_l"]) == 250  # header written before the cap (libphsh.f:4637, 4642)
+
+
+def test_workloads_are_deterministic_and_shaped():
+    from phaseshifts_b200 import workloads as W
+    a, b = W.c4_sweep(P=6, ne=10), W.c4_sweep(P=3, ne=10, first=3)
+    assert np.array_equal(a["pot"][3:], b["pot"]) and np.array_equal(a["jri"][3:], b["jri"])
+    assert a["pot"].shape == (6, 326) and a["jri"].min() >= 316 and a["jri"].max() <= 325
+    c1 = W.c1_re_fixture()
+    assert c1["pot"].shape == (2, 322) and list(c1["jri"]) == [321, 321] and c1["lmax"] == 12
+    c3 = W.c3_gold(ne=5)
+    assert c3["jri"][0] > 640 and c3["pot"].shape[1] % 2 == 0
+    c2 = W.c2_oxide(ne=7)
+    assert c2["V"].shape == (4, 250) and (c2["V"] < 0).all() and (c2["ntab"] <= 250).all()
+    c5 = W.c5_wil(P=3, ne=4)
+    assert c5["rs"].shape == (3, 200) and all(c5["rs"][i, c5["nrows"][i] - 1] < 0 for i in range(3))
+    blocks = W.read_mufftin_rel(W.RE_MUFFTIN)
+    assert len(blocks) == 2 and blocks[0]["jri"] == 321 and blocks[0]["zp"][0] == -149.8956
+
+
+def test_standin_module_surface(monkeypatch):
+    """Same names and arity as the f2py module the reference binds (phsh.py:101-113)."""
+    import inspect
+    from phaseshifts_b200 import libphsh, api
+    for fn in ("phsh_rel", "phsh_cav", "phsh_wil"):
+        assert len(inspect.signature(getattr(libphsh, fn)).parameters) == 4
+    for fn in ("cavpot", "hartfock", "hb"):
+        with pytest.raises(NotImplementedError):
+            getattr(libphsh, fn)(1, 2)
+    seen = {}
+    monkeypatch.setattr(api, "phsh_rel_file", lambda *a, **k: seen.update(args=a, kw=k))
+    monkeypatch.setenv("PHSH_B200_MAX_ENERGIES", "0")
+    monkeypatch.setenv("PHSH_B200_REAL32", "1")
+    monkeypatch.setenv("PHSH_B200_DEVICE", "3")
+    assert libphsh.phsh_rel(b"m.d   ", "p", "d", "i") is None
+    assert seen["args"] == ("m.d", "p", "d", "i")
+    assert seen["kw"]["max_energies"] == 0 and seen["kw"]["real32"] is True and seen["kw"]["device"] == 3
+    assert seen["kw"]["asbuilt"] is False

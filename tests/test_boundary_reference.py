@@ -1,0 +1,108 @@
+"""The drop-in boundary driven by the UNMODIFIED reference package (phaseshifts.phsh.Wrapper, the backend
+registry and the CLI), as far as it can be exercised in the build container: the reference lives at
+/root/reference (absent on the GPU box) and there is no GPU here, so the one call that needs the B200
+(``api.phsh_rel_file``) is replaced by the oracle's file layer -- test infrastructure standing in for the
+device, exactly like the reference's own tests monkeypatch ``cavpot`` (tests/test_phsh_helpers.py:35-50).
+Everything else -- stand-in module seeding, registry, Wrapper, split_phasout, Conphas, .phs writing -- is
+the reference's own code.  Skipped where the reference is not importable."""
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+REF = os.environ.get("PHASESHIFTS_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+RE = os.path.join(HERE, "golden", "Re0001")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "phaseshifts")),
+                                reason="reference checkout not available")
+
+
+@pytest.fixture()
+def wired(monkeypatch, tmp_path):
+    if REF not in sys.path:
+        monkeypatch.syspath_prepend(REF)
+    from phaseshifts_b200 import api, backend, libphsh, _lib
+    cls = backend.install()
+    if _lib.device_count() == 0:
+        from oracle import fortran_io as fio
+
+        def fake_rel_file(muff, phasout, dataph, inpdat, asbuilt=False, real32=False, fast=False, max_energies=250,
+                          max_jri=340, device=0):
+            fio.phsh_rel_file(muff, phasout, dataph, inpdat, real32=real32, asbuilt=asbuilt, ncap=max_energies,
+                              jri_cap=max_jri)
+        monkeypatch.setattr(api, "phsh_rel_file", fake_rel_file)
+
+    def replay_cavpot(mtz_string, slab, atomic_file, cluster_file, mufftin_file, output_file, info_file):
+        shutil.copyfile(os.path.join(RE, "mufftin_Re_slab.d"), mufftin_file)
+        with open(output_file, "w") as f:
+            f.write("0.0\n")
+        return 0.0
+    monkeypatch.setattr(libphsh, "cavpot", replay_cavpot)
+    work = tmp_path / "work"
+    work.mkdir()
+    shutil.copyfile(os.path.join(RE, "at_Re.i"), work / "at_Re.i")  # skips the hartfock step (phsh.py:195-200)
+    monkeypatch.chdir(tmp_path)
+    return cls, work
+
+
+def _leedph():
+    lines = open(os.path.join(RE, "leedph_Re.d")).read().splitlines()
+    return np.array([[float(x) for x in lines[2 * i + 1].replace("-", " -").split()] for i in range(57)])
+
+
+def test_registry_and_module_seeding(wired):
+    import phaseshifts.backends as B
+    import phaseshifts.phsh as ph
+    import phaseshifts.lib.libphsh as L
+    from phaseshifts_b200 import libphsh
+    assert L is libphsh and ph.phsh_rel is libphsh.phsh_rel and ph.phsh_cav is libphsh.phsh_cav
+    be = B.get_backend("b200")
+    assert isinstance(be, B.PhaseShiftBackend) and be.name == "b200"
+    assert "b200" in B.DEFAULT_BACKENDS and isinstance(B.get_backend("B200"), wired[0])
+    with pytest.raises(B.BackendError):
+        B.get_backend("no-such-backend")
+
+
+def test_unchanged_wrapper_through_b200_backend_matches_golden_leedph(wired):
+    import phaseshifts.backends as B
+    _, work = wired
+    files = B.get_backend("b200").autogen_from_input(os.path.join(RE, "cluster_Re_bulk.i"),
+                                                     os.path.join(RE, "cluster_Re_slab.i"), tmp_dir=str(work),
+                                                     lmax=10, format="cleed")
+    assert len(files) == 2 and all(f.endswith(".phs") for f in files)
+    gold = _leedph()
+    for f in files:
+        lines = open(f).read().splitlines()
+        assert lines[0].startswith("57 10 neng lmax")
+        got = np.array([[float(x) for x in lines[2 + 2 * i].replace("-", " -").split()] for i in range(57)])
+        assert np.abs(got - gold).max() <= 1.0001e-4
+    assert os.path.exists(work / "cluster_Re_slab_phasout.i") and os.path.exists(work / "cluster_Re_slab_inpdat.txt")
+
+
+def test_cli_route_with_energy_range(wired, monkeypatch, capsys):
+    """`python -m phaseshifts_b200 -b .. -s .. --backend b200 -r 20 600 5`: _apply_energy_range rewrites only the
+    first block's header (phsh.py:272-276), so block 1 has 117 energies and block 2 keeps 57."""
+    from phaseshifts_b200.__main__ import main
+    _, work = wired
+    rc = main(["-b", os.path.join(RE, "cluster_Re_bulk.i"), "-s", os.path.join(RE, "cluster_Re_slab.i"),
+               "-t", str(work), "-l", "10", "-f", "cleed", "-r", "20", "600", "5", "--backend", "b200"])
+    assert rc == 0
+    heads = sorted(open(work / f).readline().split()[0] for f in os.listdir(work) if f.endswith(".phs"))
+    assert heads == ["117", "57"]
+
+
+def test_backend_errors_become_backenderror(wired, monkeypatch):
+    import phaseshifts.backends as B
+    from phaseshifts_b200 import api, PhshB200Error
+
+    def boom(*a, **k):
+        raise PhshB200Error(-2, "no CUDA device available")
+    monkeypatch.setattr(api, "phsh_rel_file", boom)
+    _, work = wired
+    with pytest.raises(B.BackendError):
+        B.get_backend("b200").autogen_from_input(os.path.join(RE, "cluster_Re_bulk.i"),
+                                                 os.path.join(RE, "cluster_Re_slab.i"), tmp_dir=str(work), lmax=10,
+                                                 format="cleed")
