@@ -113,7 +113,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
-    n_pot = max(1, min(args.potentials, args.ref_potentials or 2 * threads))
+    n_pot = max(1, min(args.potentials, args.ref_potentials or 24 * threads))
     wl = make_workload(n_pot, args.energies, args.lmax, 0)
     rates, times = [], []
     for i in range(args.warmup + args.steps):
@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--energies", type=int, default=1000)
     ap.add_argument("--lmax", type=int, default=15)
     ap.add_argument("--fast", action="store_true", help="FMA-contracted integrator (not bit-faithful)")
-    ap.add_argument("--ref-potentials", type=int, default=0, help="size of the CPU sample (default 2 x host threads)")
+    ap.add_argument("--ref-potentials", type=int, default=0, help="size of the CPU sample (default 24 x host threads, ~15-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -289,7 +289,7 @@ def main():
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        n_pot = max(1, min(P, args.ref_potentials or 2 * threads))
+        n_pot = max(1, min(P, args.ref_potentials or 24 * threads))
         rate, dt, r = cpu_reference_rate(wl, n_pot, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d of %d potentials x %d energies x %d l, %.1f s" % (n_pot, P, NE, L1, dt)}

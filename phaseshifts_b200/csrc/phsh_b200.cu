@@ -2,6 +2,7 @@
 // There is deliberately no CPU implementation here: without a CUDA device every compute call fails.
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -115,9 +116,13 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
     const long target = 148L * 8;
     while (static_cast<long>(P) * chunks * lgroups < target && lgroups < L1) ++lgroups;
     const size_t smem = static_cast<size_t>(2 * jpad) * sizeof(double) + 16;
-    static const int minb = getenv("PHSH_B200_MINB") ? atoi(getenv("PHSH_B200_MINB")) : 4;
-    auto kern = minb == 5 ? rel_integrate_kernel<FAST, Real, 5> : minb == 6 ? rel_integrate_kernel<FAST, Real, 6>
-                                                                              : rel_integrate_kernel<FAST, Real, 4>;
+    // resident CTAs per SM the integrator is compiled for (register cap 65536/(128*MINB)); 6 measured fastest
+    static const int minb = getenv("PHSH_B200_MINB") ? atoi(getenv("PHSH_B200_MINB")) : 6;
+    auto kern = minb == 4   ? rel_integrate_kernel<FAST, Real, 4>
+                : minb == 5 ? rel_integrate_kernel<FAST, Real, 5>
+                : minb == 7 ? rel_integrate_kernel<FAST, Real, 7>
+                : minb == 8 ? rel_integrate_kernel<FAST, Real, 8>
+                            : rel_integrate_kernel<FAST, Real, 6>;
     if (smem > 48 * 1024) PHSH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long grid = static_cast<long>(P) * lgroups * chunks;
     kern<<<static_cast<unsigned>(grid), block, smem, st>>>(pot, pot_stride, jri, e_l0, e_l, e_stride, NE, c, lgroups,
@@ -252,22 +257,43 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
     if (rc) return rc;
     if (P == 0 || NE == 0) return 0;
     if (!e_l) e_l = e_l0;
-    cudaStream_t st;
-    PHSH_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    struct StreamGuard {
-        cudaStream_t s;
-        ~StreamGuard() { cudaStreamDestroy(s); }
-    } guard{st};
+    // two streams: kernels on `sc`, result copies on `sd`, so the D2H of slab k overlaps the integration of slab k+1
+    struct Streams {
+        cudaStream_t sc = nullptr, sd = nullptr;
+        std::vector<cudaEvent_t> ev;
+        ~Streams() {
+            for (auto e : ev) cudaEventDestroy(e);
+            if (sc) cudaStreamDestroy(sc);
+            if (sd) cudaStreamDestroy(sd);
+        }
+    } S;
+    PHSH_CUDA(cudaStreamCreateWithFlags(&S.sc, cudaStreamNonBlocking));
+    PHSH_CUDA(cudaStreamCreateWithFlags(&S.sd, cudaStreamNonBlocking));
+    cudaStream_t st = S.sc;
     const int L1 = opts->lsm + 1;
     const long ps = (pot_stride + 1) & ~1L;  // device copy padded to an even stride
     const size_t n_e = e_stride ? static_cast<size_t>(P) * e_stride : static_cast<size_t>(NE);
+    // Slabs of potentials in a geometric schedule (P/2, P/4, P/8, P/8): only the last, small slab's D2H is
+    // exposed, while the big early slabs keep the wave-quantisation loss of the integrator low.
+    std::vector<int> slabs;
+    {
+        int left = P;
+        for (int k = 0; k < 3 && left > 1024; ++k) {
+            const int n = (left + 1) / 2;
+            slabs.push_back(n);
+            left -= n;
+        }
+        if (left > 0) slabs.push_back(left);
+    }
+    const int slab = slabs[0];
+    const size_t per_pot = static_cast<size_t>(NE) * L1;
     DeviceBuf d_pot, d_jri, d_e0, d_e1, d_delta, d_raw, d_cnt;
     if ((rc = d_pot.alloc(static_cast<size_t>(P) * ps * sizeof(double), st))) return rc;
     if ((rc = d_jri.alloc(static_cast<size_t>(P) * sizeof(int), st))) return rc;
     if ((rc = d_e0.alloc(n_e * sizeof(double), st))) return rc;
     if ((rc = d_e1.alloc(n_e * sizeof(double), st))) return rc;
-    if ((rc = d_delta.alloc(static_cast<size_t>(P) * NE * L1 * sizeof(double), st))) return rc;
-    if ((rc = d_raw.alloc(static_cast<size_t>(P) * NE * L1 * 2 * sizeof(double), st))) return rc;
+    if ((rc = d_delta.alloc(static_cast<size_t>(P) * per_pot * sizeof(double), st))) return rc;
+    if ((rc = d_raw.alloc(static_cast<size_t>(kappa_out ? P : slab) * per_pot * 2 * sizeof(double), st))) return rc;
     if ((rc = d_cnt.alloc(4 * sizeof(unsigned long long), st))) return rc;
     if (ps != pot_stride) PHSH_CUDA(cudaMemsetAsync(d_pot.p, 0, static_cast<size_t>(P) * ps * sizeof(double), st));
     PHSH_CUDA(cudaMemcpy2DAsync(d_pot.p, ps * sizeof(double), pot, pot_stride * sizeof(double),
@@ -276,19 +302,32 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
     PHSH_CUDA(cudaMemcpyAsync(d_e0.p, e_l0, n_e * sizeof(double), cudaMemcpyHostToDevice, st));
     PHSH_CUDA(cudaMemcpyAsync(d_e1.p, e_l, n_e * sizeof(double), cudaMemcpyHostToDevice, st));
     PHSH_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(unsigned long long), st));
-    rc = phsh_b200_rel_batch_device(static_cast<double*>(d_pot.p), ps, static_cast<int*>(d_jri.p), P,
-                                    static_cast<double*>(d_e0.p), static_cast<double*>(d_e1.p), e_stride, NE, opts,
-                                    static_cast<double*>(d_delta.p), static_cast<double*>(d_raw.p),
-                                    static_cast<unsigned long long*>(d_cnt.p), st);
-    if (rc) return rc;
-    PHSH_CUDA(cudaMemcpyAsync(delta, d_delta.p, static_cast<size_t>(P) * NE * L1 * sizeof(double),
-                              cudaMemcpyDeviceToHost, st));
-    if (kappa_out)
-        PHSH_CUDA(cudaMemcpyAsync(kappa_out, d_raw.p, static_cast<size_t>(P) * NE * L1 * 2 * sizeof(double),
-                                  cudaMemcpyDeviceToHost, st));
+    int p0 = 0;
+    for (size_t si = 0; si < slabs.size(); p0 += slabs[si], ++si) {
+        const int n = slabs[si];
+        double* raw = static_cast<double*>(d_raw.p) + (kappa_out ? static_cast<size_t>(p0) * per_pot * 2 : 0);
+        double* dl = static_cast<double*>(d_delta.p) + static_cast<size_t>(p0) * per_pot;
+        rc = phsh_b200_rel_batch_device(static_cast<double*>(d_pot.p) + static_cast<size_t>(p0) * ps, ps,
+                                        static_cast<int*>(d_jri.p) + p0, n,
+                                        static_cast<double*>(d_e0.p) + (e_stride ? static_cast<size_t>(p0) * e_stride : 0),
+                                        static_cast<double*>(d_e1.p) + (e_stride ? static_cast<size_t>(p0) * e_stride : 0),
+                                        e_stride, NE, opts, dl, raw, static_cast<unsigned long long*>(d_cnt.p), st);
+        if (rc) return rc;
+        cudaEvent_t ev;
+        PHSH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        S.ev.push_back(ev);
+        PHSH_CUDA(cudaEventRecord(ev, st));
+        PHSH_CUDA(cudaStreamWaitEvent(S.sd, ev, 0));
+        PHSH_CUDA(cudaMemcpyAsync(delta + static_cast<size_t>(p0) * per_pot, dl, static_cast<size_t>(n) * per_pot * sizeof(double),
+                                  cudaMemcpyDeviceToHost, S.sd));
+        if (kappa_out)
+            PHSH_CUDA(cudaMemcpyAsync(kappa_out + static_cast<size_t>(p0) * per_pot * 2, raw,
+                                      static_cast<size_t>(n) * per_pot * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.sd));
+    }
     unsigned long long cnt[4] = {0, 0, 0, 0};
     PHSH_CUDA(cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
     PHSH_CUDA(cudaStreamSynchronize(st));
+    PHSH_CUDA(cudaStreamSynchronize(S.sd));
     if (counters)
         for (int i = 0; i < 4; ++i) counters[i] += cnt[i];
     return 0;

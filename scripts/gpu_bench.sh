@@ -1,5 +1,5 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_err.log | tee gpurun_out/bench2.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline'])"
-python bench.py --steps 3 --warmup 3 --fast --no-cpu-baseline 2>> gpurun_out/bench_err.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('FAST', d['value'], d['ms_per_step'], d['roofline']['frac'])"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python bench.py --steps 5 --warmup 3 2> gpurun_out/bench_err.log | tee gpurun_out/bench5.json | cut -c1-200
 tail -3 gpurun_out/bench_err.log
+python bench.py --impl reference --steps 2 --warmup 1 | tee gpurun_out/bench5_ref.json | cut -c1-200
