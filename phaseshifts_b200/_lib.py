@@ -35,6 +35,11 @@ class FileOpts(C.Structure):
     _fields_ = [("flags", C.c_int), ("max_energies", C.c_int), ("max_jri", C.c_int), ("device", C.c_int)]
 
 
+class ConphasOpts(C.Structure):
+    _fields_ = [("user", C.c_char_p), ("timestamp", C.c_char_p), ("v0", C.c_double * 4), ("has_v0", C.c_int),
+                ("device", C.c_int)]
+
+
 _dp = C.c_void_p  # raw addresses (host numpy or device tensor data_ptr)
 _SIGNATURES = {
     "phsh_b200_last_error": (C.c_char_p, []),
@@ -60,6 +65,9 @@ _SIGNATURES = {
     "phsh_b200_rel_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FileOpts)]),
     "phsh_b200_cav_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FileOpts)]),
     "phsh_b200_wil_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FileOpts)]),
+    "phsh_b200_split_phasout": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int]),
+    "phsh_b200_conphas_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int,
+                                          C.POINTER(ConphasOpts)]),
     "phsh_b200_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

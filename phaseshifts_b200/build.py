@@ -13,7 +13,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 OUT = os.path.join(_PKG, "libphsh_b200.so")
-SOURCES = ["phsh_b200.cu", "phsh_files.cpp"]
+SOURCES = ["phsh_b200.cu", "phsh_files.cpp", "phsh_conphas_files.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared"]
 

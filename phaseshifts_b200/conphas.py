@@ -1,0 +1,118 @@
+"""``Conphas`` -- mirror of ``phaseshifts.conphas.Conphas`` (phsh3 / CONPHAS) on top of the C ABI.
+
+Same constructor, setters and methods as the reference class (``phaseshifts/conphas.py:69-523``):
+``Conphas(input_files, output_file, formatting, lmax, v0_params)``, ``set_input_files``, ``set_output_file``,
+``set_lmax``, ``set_format``, ``load_data``, ``split_phasout`` (static) and ``calculate``.  Parsing, the pi-jump
+removal (on the GPU) and the cleed / curve / viperleed / plain writers live in ``libphsh_b200.so``
+(``csrc/phsh_conphas_files.cpp``, ``conphas_kernel``) and reproduce the reference's files byte for byte.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _lib
+
+HARTREE = 27.21  # conphas.py:66
+
+
+class Conphas(object):
+    def __init__(self, input_files=None, output_file=None, formatting=None, lmax=10, v0_params=None, **kwargs):
+        if input_files is None:
+            input_files = []
+        if output_file is None:
+            output_file = []
+        self.input_files = [f for f in input_files if os.path.isfile(f)]
+        self.output_file = os.path.abspath(str(output_file))
+        if 0 <= int(lmax) <= 18:
+            self.lmax = int(lmax)
+        self.v0_params = v0_params
+        self.set_format(formatting)
+        self.device = int(kwargs.pop("device", os.environ.get("PHSH_B200_DEVICE", 0)))
+        self.user = kwargs.pop("user", None)
+        self.timestamp = kwargs.pop("timestamp", None)
+        self.__dict__.update(kwargs)
+
+    # ---- setters (conphas.py:259-304)
+    def set_input_files(self, input_files=None):
+        files = [f for f in (input_files or []) if os.path.isfile(f)]
+        if files:
+            self.input_files = files
+
+    def set_output_file(self, output_file):
+        self.output_file = output_file
+
+    def set_lmax(self, lmax):
+        try:
+            self.lmax = int(lmax)
+        except TypeError:
+            pass
+
+    def set_format(self, formatting=None):
+        if str(formatting).lower() in ["cleed", "curve", "viper", "viperleed"]:
+            self.format = str(formatting).lower()
+        else:
+            self.format = None
+
+    # ---- parsing (conphas.py:171-202); kept in Python because it returns Python objects
+    def load_data(self, filename):
+        with open(filename, "r") as f:
+            f.readline()
+            (initial_energy, energy_step, n_phases, lmf) = [
+                t(s) for (t, s) in zip((float, float, int, int), f.readline().replace("-", " -").split())
+            ]
+            data_lines = [line.replace("-", " -").replace("\n", "") for line in f.readlines()]
+            data = [float(number) for number in "".join(data_lines).split()]
+        return (initial_energy, energy_step, n_phases, lmf, data)
+
+    @staticmethod
+    def split_phasout(filename, output_filenames=None):
+        """Split a ``phasout`` file into one file per atom section (conphas.py:204-257)."""
+        lib = _lib.load()
+        if isinstance(output_filenames, str):  # conphas.py:243-245
+            with open(filename, "r") as f:
+                import re
+                n = sum(1 for line in f if re.match("^[A-Za-z]", line.replace(" ", "")))
+            base = os.path.splitext(output_filenames)[0]
+            names = [base + "_%i.ph" % i for i in range(n)]
+        else:
+            names = list(output_filenames or [])
+        arr = (C.c_char_p * max(len(names), 1))(*[str(n).encode() for n in names])
+        buf = C.create_string_buffer(1 << 16)
+        rc = lib.phsh_b200_split_phasout(str(filename).encode(), arr, len(names), buf, len(buf))
+        if rc < 0:
+            msg = lib.phsh_b200_last_error().decode("utf-8", "replace")
+            if rc == _lib.EIO:
+                raise IOError(msg)
+            raise _lib.PhshB200Error(rc, msg)
+        return [s for s in buf.value.decode().split("\n") if s][:rc]
+
+    def _resolve_v0_params(self):
+        params = getattr(self, "v0_params", None)
+        if params is None:
+            return None
+        if not isinstance(params, (list, tuple)) or len(params) < 4:
+            raise ValueError("Invalid v0_params configuration: expected a list or tuple with at least 4 numeric "
+                             "elements, got {!r}".format(params))
+        try:
+            return tuple(float(v) for v in params[:4])
+        except (TypeError, ValueError) as exc:
+            raise ValueError("Invalid v0_params configuration: all first four elements must be numeric, "
+                             "got {!r}".format(params)) from exc
+
+    def calculate(self):
+        """Continuous phase shifts from the input section(s) -> ``dataph_<name>.d`` + the formatted output file."""
+        lib = _lib.load()
+        v0 = self._resolve_v0_params()
+        opts = _lib.ConphasOpts(self.user.encode() if self.user else None,
+                                self.timestamp.encode() if self.timestamp else None,
+                                (C.c_double * 4)(*(v0 or (0.0, 0.0, 0.0, 0.0))), 1 if v0 else 0, self.device)
+        files = [str(f).encode() for f in self.input_files]
+        arr = (C.c_char_p * max(len(files), 1))(*files)
+        rc = lib.phsh_b200_conphas_files(arr, len(files), str(self.output_file).encode(),
+                                         (self.format or "").encode(), int(self.lmax), C.byref(opts))
+        if rc != 0:
+            msg = lib.phsh_b200_last_error().decode("utf-8", "replace")
+            if "Malformatted" in msg or "IndexError" in msg:
+                raise IndexError(msg)
+            raise _lib.PhshB200Error(rc, msg)

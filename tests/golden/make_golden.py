@@ -7,7 +7,7 @@
    /root/reference with a stub ``libphsh``) run on
      - Re_A.ph   : the first section of the phasout the oracle (FP32-as-written) writes for the Re fixture,
      - jumps.ph  : a synthetic section with many +-pi/2 jumps, touching minus signs and an l>lmax tail,
-   in the formats cleed / curve / None, plus the dataph_<name>.d files Conphas writes.  The unwrap kernels
+   in the formats cleed / curve / None / viperleed, plus the dataph_<name>.d files Conphas writes.  The unwrap kernels
    (oracle and CUDA) and the text parsers are checked against these.
 """
 import getpass
@@ -67,7 +67,7 @@ def main():
     open(os.path.join(out, "jumps.ph"), "w").write("\n".join(rows) + "\n")
 
     for name, lmax in (("Re_A", 10), ("jumps", 12), ("jumps", 5)):
-        for fmt in ("cleed", "curve", None):
+        for fmt in ("cleed", "curve", None, "viperleed"):
             src = os.path.join(out, name + ".ph")
             dst = os.path.join(out, "%s_lmax%d_%s.out" % (name, lmax, fmt))
             c = refcon.Conphas(input_files=[src], output_file=dst, formatting=fmt, lmax=lmax)
@@ -76,7 +76,23 @@ def main():
                 lines = open(dst).read().splitlines(keepends=True)
                 lines[0] = lines[0].split("(")[0].rstrip() + "\n"
                 open(dst, "w").write("".join(lines))
+            if fmt == "viperleed":  # strip the time stamp from the header line
+                lines = open(dst).read().splitlines(keepends=True)
+                lines[0] = lines[0].rsplit(" ", 1)[0] + "\n"
+                open(dst, "w").write("".join(lines))
         shutil.move(os.path.join(out, "dataph_%s.d" % name), os.path.join(out, "dataph_%s_lmax%d.d" % (name, lmax)))
+    # two input sections in one output (the multi-atom layout of leedph files) + split_phasout itself
+    both = os.path.join(out, "two_blocks_phasout")
+    shutil.copyfile(os.path.join(tmp, "phasout"), both)
+    names = refcon.Conphas.split_phasout(both, [os.path.join(out, "split_A.ph"), os.path.join(out, "split_B.ph")])
+    assert len(names) == 2
+    dst = os.path.join(out, "two_blocks_lmax10_cleed.out")
+    refcon.Conphas(input_files=names, output_file=dst, formatting="cleed", lmax=10).calculate()
+    lines = open(dst).read().splitlines(keepends=True)
+    lines[0] = lines[0].split("(")[0].rstrip() + "\n"
+    open(dst, "w").write("".join(lines))
+    for n in ("dataph_split_A.d", "dataph_split_B.d"):
+        os.remove(os.path.join(out, n))
     shutil.rmtree(tmp)
     print("golden vectors written by", getpass.getuser())
 
