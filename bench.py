@@ -262,6 +262,17 @@ def main():
     kernel_ms = float(np.mean(kms))
     peak_tf, peak_mhz = api.fp64_peak(local)
     achieved_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+    # DRAM traffic per launch and FP64-pipe utilisation come from the committed ncu --set full capture of this very
+    # launch (profiles/); they are only quoted when the configuration is the captured one
+    traffic, ncu_pipe = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_rel_integrate_ncu_c4.json")) as f:
+            cap = json.load(f)
+        if (P, NE, args.lmax, args.fast) == (4096, 1000, 15, False):
+            traffic = cap["traffic_bytes_per_launch"]
+            ncu_pipe = cap["fp64_pipe_pct_of_peak_sustained_active"]
+    except (OSError, KeyError, ValueError):
+        pass
 
     # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H inside the timed region) ------
     pot_np, jri_np, e0_np, e1_np, out_np = pot_h.numpy(), jri_h.numpy(), e0_h.numpy(), e1_h.numpy(), out_h.numpy()
@@ -311,7 +322,10 @@ def main():
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum; algorithmic: "
+                                     "%.3g in + %.3g per-kappa scratch out)" % (pot_d.numel() * 8.0, raw_d.numel() * 8.0),
+                     "ncu_fp64_pipe_pct_of_peak_sustained_active": ncu_pipe,
                      "kernel": "rel_integrate_kernel", "kernel_ms": kernel_ms,
                      "flops_per_launch": flops_per_launch,
                      "corrector_evals_per_step": float(c[2]) / max(float(c[1]), 1.0),

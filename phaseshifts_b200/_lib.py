@@ -37,7 +37,7 @@ class FileOpts(C.Structure):
 
 class ConphasOpts(C.Structure):
     _fields_ = [("user", C.c_char_p), ("timestamp", C.c_char_p), ("v0", C.c_double * 4), ("has_v0", C.c_int),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("unwrap_all_inputs", C.c_int)]
 
 
 _dp = C.c_void_p  # raw addresses (host numpy or device tensor data_ptr)

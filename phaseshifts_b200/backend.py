@@ -22,8 +22,13 @@ from ._lib import PhshB200Error
 _INSTALLED = False
 
 
-def install(force_standin: bool = False):
-    """Wire the GPU path into an importable ``phaseshifts`` package.  Idempotent.  Returns the backend class."""
+def install(force_standin: bool = False, conphas=None):
+    """Wire the GPU path into an importable ``phaseshifts`` package.  Idempotent.  Returns the backend class.
+
+    ``conphas=True`` (or env ``PHSH_B200_CONPHAS=1``) additionally rebinds the ``Conphas`` name used by
+    ``phaseshifts.phsh`` / ``phaseshifts.wrappers`` to ``phaseshifts_b200.conphas.Conphas`` (C++ parser and
+    writers, pi-jump removal on the GPU); by default the reference's own Python ``Conphas`` keeps running.
+    """
     global _INSTALLED
     if not hasattr(builtins, "WindowsError"):
         builtins.WindowsError = OSError
@@ -54,6 +59,17 @@ def install(force_standin: bool = False):
         mod = sys.modules.get(modname)
         if mod is not None and hasattr(mod, "libphsh"):
             setattr(mod, "libphsh", _standin)
+    if conphas is None:
+        conphas = os.environ.get("PHSH_B200_CONPHAS", "0").strip().lower() not in ("", "0", "false", "no")
+    if conphas:
+        from .conphas import Conphas as _GpuConphas
+        for modname in ("phaseshifts.phsh", "phaseshifts.wrappers"):
+            try:
+                mod = importlib.import_module(modname)
+            except Exception:
+                continue
+            if hasattr(mod, "Conphas"):
+                setattr(mod, "Conphas", _GpuConphas)
     backends = importlib.import_module("phaseshifts.backends")
     cls = _make_backend(backends)
     backends.register_backend("b200", cls)

@@ -31,6 +31,8 @@ class Conphas(object):
         self.device = int(kwargs.pop("device", os.environ.get("PHSH_B200_DEVICE", 0)))
         self.user = kwargs.pop("user", None)
         self.timestamp = kwargs.pop("timestamp", None)
+        # the reference unwraps only the LAST input file in the combined output (conphas.py:434); True fixes that
+        self.unwrap_all_inputs = bool(kwargs.pop("unwrap_all_inputs", False))
         self.__dict__.update(kwargs)
 
     # ---- setters (conphas.py:259-304)
@@ -106,7 +108,8 @@ class Conphas(object):
         v0 = self._resolve_v0_params()
         opts = _lib.ConphasOpts(self.user.encode() if self.user else None,
                                 self.timestamp.encode() if self.timestamp else None,
-                                (C.c_double * 4)(*(v0 or (0.0, 0.0, 0.0, 0.0))), 1 if v0 else 0, self.device)
+                                (C.c_double * 4)(*(v0 or (0.0, 0.0, 0.0, 0.0))), 1 if v0 else 0, self.device,
+                                1 if self.unwrap_all_inputs else 0)
         files = [str(f).encode() for f in self.input_files]
         arr = (C.c_char_p * max(len(files), 1))(*files)
         rc = lib.phsh_b200_conphas_files(arr, len(files), str(self.output_file).encode(),

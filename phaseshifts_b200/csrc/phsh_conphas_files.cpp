@@ -263,6 +263,12 @@ int phsh_b200_conphas_files(const char* const* inputs, int n_inputs, const char*
         }
         fclose(f);
     }
+    // conphas.py:434 re-runs `conpha = deepcopy(phas)` for every input file, which throws away the unwrapping of
+    // all earlier files: only the last input is written unwrapped.  Reproduced unless asked otherwise.
+    if (!(opts && opts->unwrap_all_inputs))
+        for (int ii = 0; ii + 1 < n_inputs; ++ii)
+            for (size_t ie = 0; ie < conpha[ii].size(); ++ie)
+                for (size_t l = 0; l < conpha[ii][ie].size(); ++l) conpha[ii][ie][l] = secs[ii].phas[ie][l];
     for (int ii = 0; ii < n_inputs; ++ii)
         if (static_cast<int>(conpha[ii].size()) < n_phases) {
             set_error("'%s' holds fewer energies (%d) than the last input (%d) (IndexError in the reference)", inputs[ii],

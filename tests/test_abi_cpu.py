@@ -137,3 +137,34 @@ def test_standin_module_surface(monkeypatch):
     assert seen["args"] == ("m.d", "p", "d", "i")
     assert seen["kw"]["max_energies"] == 0 and seen["kw"]["real32"] is True and seen["kw"]["device"] == 3
     assert seen["kw"]["asbuilt"] is False
+
+
+def test_split_phasout_needs_no_gpu(lib, tmp_path):
+    """Conphas.split_phasout (conphas.py:204-257) is pure text handling in the C++ file layer."""
+    import filecmp
+    import shutil
+    from phaseshifts_b200.conphas import Conphas
+    con = os.path.join(ROOT, "tests", "golden", "conphas")
+    src = str(tmp_path / "phasout")
+    shutil.copyfile(os.path.join(con, "two_blocks_phasout"), src)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        # the second name is guessed from the title's last blank-separated word; PHSH_REL pads its 4A4 title with
+        # blanks, so the reference's `split(" ")[-1]` yields "" and the file is called ".ph" (conphas.py:232-234)
+        names = Conphas.split_phasout(src, [str(tmp_path / "a.ph")])
+        assert len(names) == 2 and names[0].endswith("a.ph") and names[1] == ".ph"
+        assert filecmp.cmp(names[0], os.path.join(con, "split_A.ph"), shallow=False)
+        assert filecmp.cmp(names[1], os.path.join(con, "split_B.ph"), shallow=False)
+        jumps = Conphas.split_phasout(os.path.join(con, "jumps.ph"))
+        assert jumps == ["conphas.ph"] and filecmp.cmp("conphas.ph", os.path.join(con, "jumps.ph"), shallow=False)
+    finally:
+        os.chdir(cwd)
+    with pytest.raises(IOError):
+        Conphas.split_phasout(str(tmp_path / "missing"))
+    c = Conphas(input_files=[names[0]], output_file=str(tmp_path / "o.phs"), formatting="CLEED", lmax=10)
+    assert c.format == "cleed" and c.lmax == 10
+    if lib.phsh_b200_device_count() == 0:
+        from phaseshifts_b200 import PhshB200Error
+        with pytest.raises(PhshB200Error):
+            c.calculate()

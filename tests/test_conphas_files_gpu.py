@@ -50,14 +50,24 @@ def test_split_phasout_and_two_block_output(tmp_path):
     Conphas(input_files=names, output_file=dst, formatting="cleed", lmax=10, user="u", timestamp="t").calculate()
     got, exp = _lines(dst), _lines(os.path.join(CON, "two_blocks_lmax10_cleed.out"))
     assert got[0].startswith("114 10 neng lmax (calculated by u on t)") and got[1:] == exp[1:]
-    # guessed names: last word of the title + ".ph" in the current directory (conphas.py:232-234)
+    # the reference leaves every input but the last one wrapped in the combined file (conphas.py:434); opt-in fix:
+    fixed = str(tmp_path / "two_fixed.out")
+    Conphas(input_files=names, output_file=fixed, formatting="cleed", lmax=10, user="u", timestamp="t",
+            unwrap_all_inputs=True).calculate()
+    fx = _lines(fixed)
+    row = lambda ln: [float(x) for x in ln.replace("-", " -").split()]
+    assert any(row(a)[:11] != row(b)[:11] for a, b in zip(got[2::2], fx[2::2]))    # block A differs ...
+    assert all(row(a)[11:] == row(b)[11:] for a, b in zip(got[2::2], fx[2::2]))    # ... block B does not
+    assert all(row(b)[:11] == row(b)[11:] for b in fx[2::2])                      # same potential, same phases
+    # guessed names: last blank-separated word of the title + ".ph" (conphas.py:232-234); PHSH_REL's blank-padded
+    # 4A4 titles make that "" -> ".ph" for every section, exactly as in the reference
     cwd = os.getcwd()
     os.chdir(tmp_path)
     try:
         guessed = Conphas.split_phasout(both)
     finally:
         os.chdir(cwd)
-    assert guessed == ["A.ph", "B.ph"]
+    assert guessed == [".ph", ".ph"]
     by_str = Conphas.split_phasout(both, str(tmp_path / "atom.ph"))
     assert [os.path.basename(n) for n in by_str] == ["atom_0.ph", "atom_1.ph"]
 
