@@ -108,7 +108,7 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out_fd):
     """--impl reference: the reference algorithm on the host cores (oracle port; the Fortran cannot be built here)."""
     if rank != 0:
         return
@@ -131,7 +131,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out, out_fd)
 
 
 def workload_config(args, world):
@@ -146,7 +146,17 @@ def workload_config(args, world):
             else "FAST (FMA-contracted) -- not the parity-bearing mode"}
 
 
+def emit(obj, fd):
+    """Write the ONE JSON line to the real stdout (fd saved before libraries such as NCCL could print to it)."""
+    os.write(fd, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    # everything libraries print to stdout (e.g. the "NCCL version" banner) goes to stderr; only the JSON line
+    # reaches the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -164,7 +174,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, real_stdout)
         return
 
     import torch
@@ -337,7 +347,7 @@ def main():
         "cpu_baseline": cpu,
         "parity_max_abs_err_rad": parity,
     }
-    print(json.dumps(out), flush=True)
+    emit(out, real_stdout)
 
 
 if __name__ == "__main__":
