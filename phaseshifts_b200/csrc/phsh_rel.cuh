@@ -102,7 +102,6 @@ __device__ __forceinline__ void milne_step(double (&u)[6], double (&w)[6], doubl
                                            const double POTN, const RelConsts& c, double& VC, unsigned& evals) {
     constexpr int i5 = PH, i4 = (PH + 1) % 6, i3 = (PH + 2) % 6, i2 = (PH + 3) % 6, i1 = (PH + 4) % 6,
                   i0 = (PH + 5) % 6;
-    (void)i4;
     const double T7 = 7.0, T11 = 11.0, T12 = 12.0, T14 = 14.0, T26 = 26.0, T32 = 32.0;
     double TC, VCT, pu, pw, cu, cw, up1, wp1;
     if (!FAST) {

@@ -137,7 +137,10 @@ __device__ __forceinline__ void hamming_step(double (&yP)[4], double (&yQ)[4], d
 
 // grid.x = P * chunks; dyn smem: RS ZS stage_r stage_z [rpad] + R V T1 [NR+2] doubles + 16 B + IV[NR+2] ints
 // raw[(p*NE+ie)*NL + l] = atan(-|E|^(l+1/2) S/C)
-__global__ void __launch_bounds__(128)
+#ifndef PHSH_WIL_MINB
+#define PHSH_WIL_MINB 6
+#endif
+__global__ void __launch_bounds__(128, PHSH_WIL_MINB)
     wil_integrate_kernel(const double* __restrict__ rs_g, const double* __restrict__ zs_g, long stride,
                          const int* __restrict__ nrows_arr, const double* __restrict__ z_arr,
                          const double* __restrict__ rt_arr, const double* __restrict__ e_arr, int NE, int NL, int NR,
