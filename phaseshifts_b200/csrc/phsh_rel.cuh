@@ -342,6 +342,17 @@ __global__ void __launch_bounds__(128, MINB)
     const int l_hi = L1 - 1 - lg * lper;
     const int l_lo = max(l_hi - lper + 1, 0);
 
+    // A device-resident jri cannot be validated by the host without a sync: out-of-range entries (the Fortran
+    // stops at such a block, libphsh.f:4609) produce NaN phases instead of out-of-bounds shared-memory accesses.
+    if (jri < 7 || jri > pot_stride) {
+        const int ieb = chunk * blockDim.x + threadIdx.x;
+        if (ieb < NE)
+            for (int l = l_hi; l >= l_lo; --l)
+                reinterpret_cast<double2*>(raw)[(static_cast<size_t>(p) * L1 + l) * NE + ieb] =
+                    make_double2(nan(""), nan(""));
+        return;
+    }
+
     // stage |r V| with one TMA bulk copy; rebuild r(j) meanwhile
     const uint32_t bytes = static_cast<uint32_t>(((jri + 1) & ~1) * sizeof(double));
     if (threadIdx.x == 0) mbar_init(bar, 1);

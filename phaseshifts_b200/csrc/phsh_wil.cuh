@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128, PHSH_WIL_MINB)
 
     const int chunk = blockIdx.x % chunks;
     const int p = blockIdx.x / chunks;
-    const int nrows = min(nrows_arr[p], 200);
+    const int nrows = max(0, min(min(nrows_arr[p], 200), static_cast<int>(stride)));
     const double Z = z_arr[p], RT = rt_arr[p];
     const uint32_t bytes = static_cast<uint32_t>(((nrows + 1) & ~1) * sizeof(double));
     if (threadIdx.x == 0) mbar_init(bar, 1);
