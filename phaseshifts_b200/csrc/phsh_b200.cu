@@ -257,17 +257,21 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
     if (rc) return rc;
     if (P == 0 || NE == 0) return 0;
     if (!e_l) e_l = e_l0;
-    // two streams: kernels on `sc`, result copies on `sd`, so the D2H of slab k overlaps the integration of slab k+1
+    // Three streams: slabs alternate between two compute streams (`sc`, `sc2`) so that the draining tail of one
+    // slab's integrator overlaps the head of the next, and results are copied on `sd`, so that the D2H of slab k
+    // overlaps the integration of slab k+1.
     struct Streams {
-        cudaStream_t sc = nullptr, sd = nullptr;
+        cudaStream_t sc = nullptr, sc2 = nullptr, sd = nullptr;
         std::vector<cudaEvent_t> ev;
         ~Streams() {
             for (auto e : ev) cudaEventDestroy(e);
             if (sc) cudaStreamDestroy(sc);
+            if (sc2) cudaStreamDestroy(sc2);
             if (sd) cudaStreamDestroy(sd);
         }
     } S;
     PHSH_CUDA(cudaStreamCreateWithFlags(&S.sc, cudaStreamNonBlocking));
+    PHSH_CUDA(cudaStreamCreateWithFlags(&S.sc2, cudaStreamNonBlocking));
     PHSH_CUDA(cudaStreamCreateWithFlags(&S.sd, cudaStreamNonBlocking));
     cudaStream_t st = S.sc;
     const int L1 = opts->lsm + 1;
@@ -285,7 +289,6 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
         }
         if (left > 0) slabs.push_back(left);
     }
-    const int slab = slabs[0];
     const size_t per_pot = static_cast<size_t>(NE) * L1;
     DeviceBuf d_pot, d_jri, d_e0, d_e1, d_delta, d_raw, d_cnt;
     if ((rc = d_pot.alloc(static_cast<size_t>(P) * ps * sizeof(double), st))) return rc;
@@ -293,7 +296,7 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
     if ((rc = d_e0.alloc(n_e * sizeof(double), st))) return rc;
     if ((rc = d_e1.alloc(n_e * sizeof(double), st))) return rc;
     if ((rc = d_delta.alloc(static_cast<size_t>(P) * per_pot * sizeof(double), st))) return rc;
-    if ((rc = d_raw.alloc(static_cast<size_t>(kappa_out ? P : slab) * per_pot * 2 * sizeof(double), st))) return rc;
+    if ((rc = d_raw.alloc(static_cast<size_t>(P) * per_pot * 2 * sizeof(double), st))) return rc;
     if ((rc = d_cnt.alloc(4 * sizeof(unsigned long long), st))) return rc;
     if (ps != pot_stride) PHSH_CUDA(cudaMemsetAsync(d_pot.p, 0, static_cast<size_t>(P) * ps * sizeof(double), st));
     PHSH_CUDA(cudaMemcpy2DAsync(d_pot.p, ps * sizeof(double), pot, pot_stride * sizeof(double),
@@ -302,10 +305,16 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
     PHSH_CUDA(cudaMemcpyAsync(d_e0.p, e_l0, n_e * sizeof(double), cudaMemcpyHostToDevice, st));
     PHSH_CUDA(cudaMemcpyAsync(d_e1.p, e_l, n_e * sizeof(double), cudaMemcpyHostToDevice, st));
     PHSH_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(unsigned long long), st));
+    cudaEvent_t ready;  // inputs are on the device
+    PHSH_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    S.ev.push_back(ready);
+    PHSH_CUDA(cudaEventRecord(ready, st));
+    PHSH_CUDA(cudaStreamWaitEvent(S.sc2, ready, 0));
     int p0 = 0;
     for (size_t si = 0; si < slabs.size(); p0 += slabs[si], ++si) {
         const int n = slabs[si];
-        double* raw = static_cast<double*>(d_raw.p) + (kappa_out ? static_cast<size_t>(p0) * per_pot * 2 : 0);
+        cudaStream_t st = (si & 1) ? S.sc2 : S.sc;
+        double* raw = static_cast<double*>(d_raw.p) + static_cast<size_t>(p0) * per_pot * 2;
         double* dl = static_cast<double*>(d_delta.p) + static_cast<size_t>(p0) * per_pot;
         rc = phsh_b200_rel_batch_device(static_cast<double*>(d_pot.p) + static_cast<size_t>(p0) * ps, ps,
                                         static_cast<int*>(d_jri.p) + p0, n,
@@ -325,6 +334,7 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
                                       static_cast<size_t>(n) * per_pot * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.sd));
     }
     unsigned long long cnt[4] = {0, 0, 0, 0};
+    PHSH_CUDA(cudaStreamSynchronize(S.sc2));
     PHSH_CUDA(cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
     PHSH_CUDA(cudaStreamSynchronize(st));
     PHSH_CUDA(cudaStreamSynchronize(S.sd));
