@@ -312,8 +312,11 @@ def main():
         threads = host_threads()
         n_pot = max(1, min(P, args.ref_potentials or 24 * threads))
         rate, dt, r = cpu_reference_rate(wl, n_pot, threads)
+        rate1, dt1, _ = cpu_reference_rate(wl, min(4, n_pot), 1)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d of %d potentials x %d energies x %d l, %.1f s" % (n_pot, P, NE, L1, dt)}
+               "sample": "%d of %d potentials x %d energies x %d l, %.1f s" % (n_pot, P, NE, L1, dt),
+               "single_thread_value": rate1,
+               "single_thread_sample": "%d potentials, %.1f s" % (min(4, n_pot), dt1)}
         from oracle import oracle as orc
         ref = np.stack([orc.conphas(x) for x in r["jf"]])
         parity = float(np.abs(out_np[:n_pot] - ref).max())

@@ -109,12 +109,16 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
                                 const double* e_l, long e_stride, int NE, const RelConsts& c, int jpad, double* raw,
                                 unsigned long long* counters, cudaStream_t st) {
     const int L1 = c.lsm + 1;
+    static const int env_block = getenv("PHSH_B200_BLOCK") ? atoi(getenv("PHSH_B200_BLOCK")) : 0;
+    static const int env_lgroups = getenv("PHSH_B200_LGROUPS") ? atoi(getenv("PHSH_B200_LGROUPS")) : 0;
     int block = NE >= 128 ? 128 : ((NE + 31) / 32) * 32;
+    if (env_block == 32 || env_block == 64 || env_block == 128) block = std::min(block, env_block);
     const int chunks = (NE + block - 1) / block;
     // enough CTAs to fill 148 SMs several times over; otherwise split the l range across CTAs
     int lgroups = 1;
     const long target = 148L * 8;
     while (static_cast<long>(P) * chunks * lgroups < target && lgroups < L1) ++lgroups;
+    if (env_lgroups > 0) lgroups = std::min(std::max(lgroups, env_lgroups), L1);
     const size_t smem = static_cast<size_t>(2 * jpad) * sizeof(double) + 16;
     // resident CTAs per SM the integrator is compiled for (register cap 65536/(128*MINB)); 6 measured fastest
     static const int minb = getenv("PHSH_B200_MINB") ? atoi(getenv("PHSH_B200_MINB")) : 6;
