@@ -106,3 +106,47 @@ def test_backend_errors_become_backenderror(wired, monkeypatch):
         B.get_backend("b200").autogen_from_input(os.path.join(RE, "cluster_Re_bulk.i"),
                                                  os.path.join(RE, "cluster_Re_slab.i"), tmp_dir=str(work), lmax=10,
                                                  format="cleed")
+
+
+def test_duplicate_caller_wrappers_and_factory(wired):
+    """The older call site (wrappers.BVHWrapper, reached through factories.PhaseshiftFactory; wrappers.py:632-699)
+    binds the same three callables and must land on the same stand-in."""
+    import phaseshifts.wrappers as W
+    from phaseshifts.factories import PhaseshiftFactory
+    from phaseshifts_b200 import libphsh
+    from phaseshifts_b200.backend import install
+    install()  # rebinding of an already imported phaseshifts.wrappers
+    assert W.phsh_rel is libphsh.phsh_rel and W.phsh_cav is libphsh.phsh_cav and W.phsh_wil is libphsh.phsh_wil
+    _, work = wired
+    fac = PhaseshiftFactory("bvh")
+    assert isinstance(fac.backend, W.BVHWrapper)
+    # The old wrapper pairs the phasout sections with the tags of slab AND bulk atoms (wrappers.py:609-610), so on
+    # this two-atom input it runs out of sections after the slab's two atoms -- the reference's own IndexError
+    # (wrappers.py:125), raised only after our phsh_rel and its Conphas have produced both .phs files.
+    with pytest.raises(IndexError):
+        fac.backend.autogen_from_input(os.path.join(RE, "cluster_Re_bulk.i"), os.path.join(RE, "cluster_Re_slab.i"),
+                                       tmp_dir=str(work), lmax=10, format="cleed")
+    files = sorted(str(work / f) for f in os.listdir(work) if f.endswith(".phs"))
+    assert len(files) == 2
+    gold = _leedph()
+    for f in files:
+        lines = open(f).read().splitlines()
+        got = np.array([[float(x) for x in lines[2 + 2 * i].replace("-", " -").split()] for i in range(57)])
+        assert np.abs(got - gold).max() <= 1.0001e-4
+
+
+def test_optional_gpu_conphas_rebinding(wired, monkeypatch):
+    """install(conphas=True) swaps the Conphas name used by the Wrapper for the C++/GPU mirror class."""
+    import phaseshifts.phsh as ph
+    import phaseshifts.conphas as refcon
+    from phaseshifts_b200.backend import install
+    from phaseshifts_b200.conphas import Conphas as GpuConphas
+    orig = ph.Conphas
+    try:
+        install(conphas=True)
+        assert ph.Conphas is GpuConphas
+        for name in ("split_phasout", "calculate", "load_data", "set_input_files", "set_output_file", "set_lmax",
+                     "set_format"):
+            assert hasattr(GpuConphas, name) and hasattr(refcon.Conphas, name)
+    finally:
+        monkeypatch.setattr(ph, "Conphas", orig)
