@@ -215,7 +215,7 @@ int phsh_b200_rel_integrate_device(const double* pot, long pot_stride, const int
 
 int phsh_b200_rel_energy_axis_device(const double* raw, int P, int NE, const phsh_b200_rel_opts* opts, double* delta,
                                      void* stream) {
-    if (!opts || P < 0 || NE < 0 || opts->lsm < 0) {
+    if (!opts || P < 0 || NE < 0 || opts->lsm < 0 || opts->lsm > 63) {
         set_error("bad arguments");
         return PHSH_B200_EINVAL;
     }
