@@ -260,8 +260,9 @@ template <> struct RMath<double> {
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
 };
 template <> struct RMath<float> {
-    // libm's sinf/cosf/atanf are correctly rounded in all but vanishingly rare cases; a double
-    // evaluation rounded once to float reproduces that, CUDA's own sinf (2 ulp) would not.
+    // Correctly rounded REAL*4 elementary functions (double evaluation rounded once).  glibc's sinf/cosf/atanf
+    // are NOT correctly rounded, so this agrees with a gfortran build of the reference to a few float ulps
+    // (<= 2e-6 rad after the matching arithmetic), not bit for bit -- measured in tests/test_files_gpu.py.
     static __device__ __forceinline__ float sqrt_(float x) { return __fsqrt_rn(x); }
     static __device__ __forceinline__ float sin_(float x) { return static_cast<float>(sin(static_cast<double>(x))); }
     static __device__ __forceinline__ float cos_(float x) { return static_cast<float>(cos(static_cast<double>(x))); }
