@@ -69,6 +69,7 @@ _SIGNATURES = {
     "phsh_b200_conphas_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int,
                                           C.POINTER(ConphasOpts)]),
     "phsh_b200_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "phsh_b200_selftest_div075": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

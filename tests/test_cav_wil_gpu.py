@@ -60,3 +60,15 @@ def test_wil_grid_sizes(oracle, NR, NL):
     ref = oracle.wil_batch(w["rs"], w["zs"], w["nrows"], w["Z"], w["RT"], w["e"], NL=NL, NR=NR)["del"]
     ref = np.stack([oracle.conphas(x) for x in ref])
     assert np.abs(got - ref).max() <= TOL
+
+
+def test_exact_division_by_0p75_selftest():
+    """The wil kernel replaces the IEEE division x/0.75 of the Hamming predictor (phsh2.f:556-557) by a
+    3-instruction sequence that is provably correctly rounded; check it bit for bit on 2e8 patterns as well."""
+    import ctypes
+    from phaseshifts_b200 import _lib
+    lib = _lib.load()
+    for seed in (1, 2):
+        bad = ctypes.c_ulonglong(123)
+        _lib.check(lib.phsh_b200_selftest_div075(100_000_000, seed, ctypes.byref(bad), 0))
+        assert bad.value == 0
