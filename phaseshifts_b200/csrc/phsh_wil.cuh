@@ -275,6 +275,10 @@ __global__ void __launch_bounds__(128, PHSH_WIL_MINB)
     const double TZ = M::mul(2.0, Z);
     const double EP = M::sub(M::sub(E, V[4]), M::div(TZ, R[4]));
     double A1 = 1.0;
+    // F44(l+1) of this l is F44(l) of the next, F45(l) of this l is F45(l-1) of the next: evaluate each once
+    // (same function, same arguments => the same bits the reference's four calls per l return)
+    double f44_l = f44_dev(0, T4);
+    double f45_lm1 = -f44_l;  // F45(-1, x) = -F44(0, x)  (phsh2.f:709)
     for (int LP1 = 1; LP1 <= NL; ++LP1) {
         const int L = LP1 - 1;
         const int TLP1s = 2 * LP1;
@@ -337,8 +341,12 @@ __global__ void __launch_bounds__(128, PHSH_WIL_MINB)
         // matching at R(NR) (phsh2.f:356-368)
         const double T5 = powi_dev(RN, LP1);
         const double UT = M::add(M::div(fPl, TX), M::div(M::mul(static_cast<double>(L), yPl), RN));
-        const double S = M::mul(M::add(M::mul(f44_dev(L, T4), yQl), M::mul(M::mul(T3, f44_dev(LP1, T4)), yPl)), T5);
-        const double Cc = M::div(M::mul(M::sub(M::mul(f45_dev(L, T4), UT), M::mul(M::mul(T3, f45_dev(L - 1, T4)), yPl)), RN), T5);
+        const double f44_lp1 = f44_dev(LP1, T4);
+        const double f45_l = f45_dev(L, T4);
+        const double S = M::mul(M::add(M::mul(f44_l, yQl), M::mul(M::mul(T3, f44_lp1), yPl)), T5);
+        const double Cc = M::div(M::mul(M::sub(M::mul(f45_l, UT), M::mul(M::mul(T3, f45_lm1), yPl)), RN), T5);
+        f44_l = f44_lp1;
+        f45_lm1 = f45_l;
         const double D = atan(M::div(M::mul(-pow(fabs(E), M::sub(static_cast<double>(LP1), 0.5)), S), Cc));
         if (active) raw[(static_cast<size_t>(p) * NE + ie) * NL + L] = D;
     }
