@@ -87,3 +87,46 @@ def phsh_rel_sweep(pot, jri, energies_ryd, lmax, *, gather=True, compute=None, g
     if d is not None and d.get_backend(group) == "nccl":
         t = t.cuda(int(os.environ.get("LOCAL_RANK", rank)))
     return gather_blocks(t, P, group=group).cpu().numpy()
+
+
+def phsh_rel_batch_multi(pot, jri, energies_ryd, lmax, *, devices=None, **kwargs):
+    """Single-process variant: shard ``pot`` [P, J] (host array) over several GPUs of this process.
+
+    One host thread per device calls the re-entrant host-buffer entry point (ctypes releases the GIL, every call
+    owns its streams), each writing its slice of one pinned-or-pageable result array -- the "gather to host" of
+    the sweep.  ``devices`` defaults to every visible GPU.  Same keyword arguments as ``api.phsh_rel_batch``.
+    """
+    import threading
+    from . import _lib, api
+    pot = np.ascontiguousarray(pot, dtype=np.float64)
+    P = pot.shape[0]
+    jri = np.ascontiguousarray(np.broadcast_to(np.asarray(jri, dtype=np.int32), (P,)))
+    e = np.ascontiguousarray(energies_ryd, dtype=np.float64)
+    e0 = kwargs.pop("energies_l0", None)
+    e0 = None if e0 is None else np.ascontiguousarray(e0, dtype=np.float64)
+    if devices is None:
+        devices = list(range(max(1, _lib.device_count())))
+    out = kwargs.pop("out", None)
+    if out is None:
+        out = np.empty((P, e.shape[-1], int(lmax) + 1))
+    errors = []
+
+    def work(k, dev):
+        a, b = shard_range(P, k, len(devices))
+        if b <= a:
+            return
+        try:
+            api.phsh_rel_batch(pot[a:b], jri[a:b], e[a:b] if e.ndim == 2 else e, lmax,
+                               energies_l0=None if e0 is None else (e0[a:b] if e0.ndim == 2 else e0),
+                               device=dev, out=out[a:b], **kwargs)
+        except Exception as exc:  # re-raised in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(k, d)) for k, d in enumerate(devices)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out

@@ -111,3 +111,18 @@ def test_bad_inputs_on_device_give_nan_not_faults(oracle):
     ok = ~np.isnan(ref)
     assert np.abs(got[ok] - ref[ok]).max() <= TOL
     assert abs(abs(got[0, 0, 0]) - float(np.float32(3.141592654)) / 2) < 1e-12
+
+
+def test_single_process_multi_device_sharding(oracle):
+    """phsh_rel_batch_multi: one host thread per device writing its slice of one result array (here the same
+    device several times, which exercises the concurrency on a one-GPU box as well)."""
+    from phaseshifts_b200 import workloads, _lib
+    from phaseshifts_b200.distributed import phsh_rel_batch_multi
+    w = workloads.c4_sweep(P=11, ne=90, lmax=6)
+    g = w["grid"]
+    n = _lib.device_count()
+    devs = list(range(n)) if n > 1 else [0, 0, 0]
+    got = phsh_rel_batch_multi(w["pot"], w["jri"], g["e_l"], 6, energies_l0=g["e_l0"], unwrap=True, devices=devs)
+    ref = oracle.rel_batch(w["pot"], w["jri"], g["e_l0"], g["e_l"], lsm=6)["jf"]
+    ref = np.stack([oracle.conphas(x) for x in ref])
+    assert np.abs(got - ref).max() <= TOL
