@@ -111,15 +111,21 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
     const int L1 = c.lsm + 1;
     static const int env_block = getenv("PHSH_B200_BLOCK") ? atoi(getenv("PHSH_B200_BLOCK")) : 0;
     static const int env_lgroups = getenv("PHSH_B200_LGROUPS") ? atoi(getenv("PHSH_B200_LGROUPS")) : 0;
+    static const int env_pack = getenv("PHSH_B200_PACK") ? atoi(getenv("PHSH_B200_PACK")) : 1;
     int block = NE >= 128 ? 128 : ((NE + 31) / 32) * 32;
     if (env_block == 32 || env_block == 64 || env_block == 128) block = std::min(block, env_block);
-    const int chunks = (NE + block - 1) / block;
+    // Packed lanes (a CTA may straddle potentials) when each potential still fills at least half a CTA, so that
+    // at most 3 potential tables are staged per CTA; otherwise every potential gets its own CTAs.
+    const bool packed = env_pack && NE >= 64 && P > 1;
+    const int lane_stride = packed ? NE : ((NE + block - 1) / block) * block;
+    const int kmax = packed ? (block - 2) / NE + 2 : 1;
+    const long ctas = (static_cast<long>(P) * lane_stride + block - 1) / block;
     // enough CTAs to fill 148 SMs several times over; otherwise split the l range across CTAs
     int lgroups = 1;
     const long target = 148L * 8;
-    while (static_cast<long>(P) * chunks * lgroups < target && lgroups < L1) ++lgroups;
+    while (ctas * lgroups < target && lgroups < L1) ++lgroups;
     if (env_lgroups > 0) lgroups = std::min(std::max(lgroups, env_lgroups), L1);
-    const size_t smem = static_cast<size_t>(2 * jpad) * sizeof(double) + 16;
+    const size_t smem = static_cast<size_t>(kmax + 1) * jpad * sizeof(double) + 16;
     // resident CTAs per SM the integrator is compiled for (register cap 65536/(128*MINB)); 6 measured fastest
     static const int minb = getenv("PHSH_B200_MINB") ? atoi(getenv("PHSH_B200_MINB")) : 6;
     auto kern = minb == 4   ? rel_integrate_kernel<FAST, Real, 4>
@@ -128,9 +134,13 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
                 : minb == 8 ? rel_integrate_kernel<FAST, Real, 8>
                             : rel_integrate_kernel<FAST, Real, 6>;
     if (smem > 48 * 1024) PHSH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long grid = static_cast<long>(P) * lgroups * chunks;
-    kern<<<static_cast<unsigned>(grid), block, smem, st>>>(pot, pot_stride, jri, e_l0, e_l, e_stride, NE, c, lgroups,
-                                                            chunks, jpad, raw, counters);
+    const long grid = ctas * lgroups;
+    if (grid > 0x7fffffffL) {
+        set_error("batch too large for one launch (%ld CTAs); split the potentials", grid);
+        return PHSH_B200_EINVAL;
+    }
+    kern<<<static_cast<unsigned>(grid), block, smem, st>>>(pot, pot_stride, jri, e_l0, e_l, e_stride, NE, P, c, lgroups,
+                                                            lane_stride, kmax, jpad, raw, counters);
     PHSH_CUDA(cudaGetLastError());
     return 0;
 }
@@ -158,7 +168,7 @@ static int rel_check(long pot_stride, int P, int NE, const phsh_b200_rel_opts* o
         set_error("bad radial grid xs=%g dx=%g", o->xs, o->dx);
         return PHSH_B200_EINVAL;
     }
-    if (static_cast<size_t>(2 * (pot_stride + 2)) * sizeof(double) + 16 > 200 * 1024) {
+    if (static_cast<size_t>(4 * (pot_stride + 2)) * sizeof(double) + 16 > 200 * 1024) {
         set_error("pot_stride=%ld does not fit the shared-memory staging buffer", pot_stride);
         return PHSH_B200_EINVAL;
     }

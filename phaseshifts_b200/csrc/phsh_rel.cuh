@@ -7,8 +7,8 @@
 //   conphas pi-jump removal                       phaseshifts/conphas.py:437-456
 //
 // Design (B200-first, nothing here is a dense contraction, so no tensor cores):
-//   kernel A  rel_integrate_kernel: one CTA = one muffin-tin potential x one tile of
-//             blockDim.x energies x a group of l.  |r V(r)| is staged ONCE into shared
+//   kernel A  rel_integrate_kernel: one CTA = blockDim.x consecutive (potential, energy)
+//             lanes (one potential, or the tail of one and the head of the next) x a group of l.  |r V(r)| is staged ONCE into shared
 //             memory by a TMA bulk copy (cp.async.bulk + mbarrier) and reused by every
 //             energy, l and kappa of the CTA; r(j) is rebuilt next to it by the same
 //             repeated multiplication T=T*TDX the Fortran uses.  One lane = one energy,
@@ -325,19 +325,24 @@ __device__ __forceinline__ Real sbfit_match(const Bessel<Real>& b, double T, int
 template <bool FAST, class Real, int MINB>
 __global__ void __launch_bounds__(128, MINB)
     rel_integrate_kernel(const double* __restrict__ pot, long pot_stride, const int* __restrict__ jri_arr,
-                         const double* __restrict__ e_l0, const double* __restrict__ e_l, long e_stride, int NE,
-                         const __grid_constant__ RelConsts c, int lgroups, int chunks, int jpad,
+                         const double* __restrict__ e_l0, const double* __restrict__ e_l, long e_stride, int NE, int P,
+                         const __grid_constant__ RelConsts c, int lgroups, int lane_stride, int kmax, int jpad,
                          double* __restrict__ raw, unsigned long long* __restrict__ counters) {
+    // Lanes are the flattened (potential, energy) pairs g = p*lane_stride + ie.  With lane_stride == NE (packed,
+    // used when NE is large enough) a CTA's 128 lanes may straddle up to kmax potentials, so no lane is left idle
+    // at the end of every potential's energy axis; with lane_stride a multiple of blockDim a CTA never straddles.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* pot_s = reinterpret_cast<double*>(smem_raw);
-    double* r_s = pot_s + jpad;
+    double* pot_s = reinterpret_cast<double*>(smem_raw);  // [kmax][jpad]
+    double* r_s = pot_s + static_cast<size_t>(kmax) * jpad;
     uint64_t* bar = reinterpret_cast<uint64_t*>(r_s + jpad);
 
     const int L1 = c.lsm + 1;
-    const int chunk = blockIdx.x % chunks;
-    const int lg = (blockIdx.x / chunks) % lgroups;
-    const int p = blockIdx.x / (chunks * lgroups);
-    const int jri = jri_arr[p];
+    const int lg = blockIdx.x % lgroups;
+    const long g0 = static_cast<long>(blockIdx.x / lgroups) * blockDim.x;
+    const long total = static_cast<long>(P) * lane_stride;
+    const int p_first = static_cast<int>(g0 / lane_stride);
+    const int p_last = static_cast<int>(min((g0 + blockDim.x - 1) / lane_stride, static_cast<long>(P - 1)));
+    const int npot = min(p_last - p_first + 1, kmax);
     const int lper = (L1 + lgroups - 1) / lgroups;
     // costly (high-l) groups are scheduled first
     const int l_hi = L1 - 1 - lg * lper;
@@ -345,63 +350,84 @@ __global__ void __launch_bounds__(128, MINB)
 
     // A device-resident jri cannot be validated by the host without a sync: out-of-range entries (the Fortran
     // stops at such a block, libphsh.f:4609) produce NaN phases instead of out-of-bounds shared-memory accesses.
-    if (jri < 7 || jri > pot_stride) {
-        const int ieb = chunk * blockDim.x + threadIdx.x;
-        if (ieb < NE)
-            for (int l = l_hi; l >= l_lo; --l)
-                reinterpret_cast<double2*>(raw)[(static_cast<size_t>(p) * L1 + l) * NE + ieb] =
-                    make_double2(nan(""), nan(""));
-        return;
+    int jmax = 0;
+    for (int k = 0; k < npot; ++k) {
+        const int j = jri_arr[p_first + k];
+        if (j >= 7 && j <= pot_stride) jmax = max(jmax, j);
     }
 
-    // stage |r V| with one TMA bulk copy; rebuild r(j) meanwhile
-    const uint32_t bytes = static_cast<uint32_t>(((jri + 1) & ~1) * sizeof(double));
+    // stage |r V| of the CTA's potentials with TMA bulk copies; rebuild r(j) meanwhile
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && jmax > 0) {
+        uint32_t bytes = 0;
+        for (int k = 0; k < npot; ++k) {
+            const int j = jri_arr[p_first + k];
+            if (j >= 7 && j <= pot_stride) bytes += static_cast<uint32_t>(((j + 1) & ~1) * sizeof(double));
+        }
         mbar_expect_tx(bar, bytes);
-        tma_bulk_g2s(pot_s, pot + static_cast<size_t>(p) * pot_stride, bytes, bar);
+        for (int k = 0; k < npot; ++k) {
+            const int j = jri_arr[p_first + k];
+            if (j >= 7 && j <= pot_stride)
+                tma_bulk_g2s(pot_s + static_cast<size_t>(k) * jpad, pot + static_cast<size_t>(p_first + k) * pot_stride,
+                             static_cast<uint32_t>(((j + 1) & ~1) * sizeof(double)), bar);
+        }
     }
     if (threadIdx.x == blockDim.x - 1) {
         double T = c.T6;  // r(6)
-        for (int j = 6; j < jri; ++j) {  // table index j <-> r(j+1)
+        for (int j = 6; j < jmax; ++j) {  // table index j <-> r(j+1)
             T = dmul(T, c.TDX);
             r_s[j] = T;
         }
     }
-    mbar_wait(bar, 0);
-    for (int j = threadIdx.x; j < jri; j += blockDim.x) pot_s[j] = fabs(pot_s[j]);  // ZP=|ZP| (libphsh.f:4618-4622)
+    if (jmax > 0) mbar_wait(bar, 0);
+    for (int k = 0; k < npot; ++k) {
+        const int j = jri_arr[p_first + k];
+        if (j >= 7 && j <= pot_stride)
+            for (int i = threadIdx.x; i < j; i += blockDim.x) {  // ZP=|ZP| (libphsh.f:4618-4622)
+                double* q = pot_s + static_cast<size_t>(k) * jpad + i;
+                *q = fabs(*q);
+            }
+    }
     __syncthreads();
 
-    const int ie = chunk * blockDim.x + threadIdx.x;
-    const bool active = ie < NE;
-    const int iec = active ? ie : NE - 1;
+    const long g = g0 + threadIdx.x;
+    const int p = static_cast<int>(min(g / lane_stride, static_cast<long>(P - 1)));
+    const int ie = static_cast<int>(g - static_cast<long>(p) * lane_stride);
+    const bool active = g < total && ie < NE && (p - p_first) < npot;
+    const int jri = jri_arr[p];
+    const bool valid = jri >= 7 && jri <= pot_stride;
+    const double* __restrict__ pot_l = pot_s + static_cast<size_t>(min(p - p_first, npot - 1)) * jpad;
+    const int iec = (active ? ie : 0);
     const double E0 = e_l0[static_cast<size_t>(p) * e_stride + iec];
     const double E1 = e_l[static_cast<size_t>(p) * e_stride + iec];
-    const double R = r_s[jri - 1];
     const bool asbuilt = (c.flags & 0x1) != 0;
     const double c4pi = static_cast<double>(12.5663706f);
     unsigned steps = 0, evals = 0, calls = 0;
 
-    for (int l = l_hi; l >= l_lo; --l) {
-        const double E = (l == 0) ? E0 : E1;
-        // kappa = -(l+1) first, then kappa = l.  One copy of the integrator in the instruction stream: with two
-        // inlined copies the unrolled Milne phases overflow the instruction cache (measured 287 vs 220 ms).
-        double dlu = 0.0, dld = 0.0;
-        const int nk = l > 0 ? 2 : 1;
+    if (active && !valid) {
+        for (int l = l_hi; l >= l_lo; --l)
+            reinterpret_cast<double2*>(raw)[(static_cast<size_t>(p) * L1 + l) * NE + ie] = make_double2(nan(""), nan(""));
+    } else if (active) {
+        const double R = r_s[jri - 1];
+        for (int l = l_hi; l >= l_lo; --l) {
+            const double E = (l == 0) ? E0 : E1;
+            // kappa = -(l+1) first, then kappa = l.  One copy of the integrator in the instruction stream: with
+            // two inlined copies the unrolled Milne phases overflow the instruction cache (measured 287 vs 220 ms).
+            double dlu = 0.0, dld = 0.0;
+            const int nk = l > 0 ? 2 : 1;
 #pragma unroll 1
-        for (int s = 0; s < nk; ++s) {
-            const double v = dlgkap_dev<FAST>(pot_s, r_s, jri, E, s == 0 ? -(l + 1) : l, c, steps, evals) / c4pi;
-            ++calls;
-            if (s == 0)
-                dlu = v;
-            else
-                dld = v;
-        }
-        const Bessel<Real> b = sbfit_bessel<Real>(E, R, l, asbuilt);
-        const Real JFU = sbfit_match<Real>(b, dlu, l);
-        const Real JFD = l > 0 ? sbfit_match<Real>(b, dld, l) : JFU;
-        if (active) {
+            for (int s = 0; s < nk; ++s) {
+                const double v = dlgkap_dev<FAST>(pot_l, r_s, jri, E, s == 0 ? -(l + 1) : l, c, steps, evals) / c4pi;
+                ++calls;
+                if (s == 0)
+                    dlu = v;
+                else
+                    dld = v;
+            }
+            const Bessel<Real> b = sbfit_bessel<Real>(E, R, l, asbuilt);
+            const Real JFU = sbfit_match<Real>(b, dlu, l);
+            const Real JFD = l > 0 ? sbfit_match<Real>(b, dld, l) : JFU;
             double2 o;
             o.x = static_cast<double>(JFD);
             o.y = static_cast<double>(JFU);
@@ -409,7 +435,7 @@ __global__ void __launch_bounds__(128, MINB)
         }
     }
     if (counters != nullptr) {
-        if (!active) steps = evals = calls = 0;
+        __syncwarp();
         for (int o = 16; o > 0; o >>= 1) {
             steps += __shfl_down_sync(0xffffffffu, steps, o);
             evals += __shfl_down_sync(0xffffffffu, evals, o);
