@@ -1,2 +1,6 @@
-python -m pytest tests/test_rel_gpu.py tests/test_full_size_gpu.py tests/test_robustness_gpu.py -x -q 2>&1 | tail -3
-for cfg in "1 6" "0 6" "1 5" "0 5" "1 4"; do set -- $cfg; PHSH_B200_PACK=$1 PHSH_B200_MINB=$2 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('pack $1 minb $2', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'])"; done
+set -x
+for n in 8 4 2; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2954$n bench.py --gpus $n --steps 3 --warmup 3 2> gpurun_out/bench_n${n}_err.log > gpurun_out/bench_n$n.json
+cut -c1-200 gpurun_out/bench_n$n.json
+done
+python -m pytest tests/test_robustness_gpu.py -q -k multi_device 2>&1 | tail -2
