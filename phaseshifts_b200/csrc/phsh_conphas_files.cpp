@@ -14,6 +14,8 @@
 #include <cstring>
 #include <ctime>
 #include <fstream>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -109,8 +111,8 @@ struct Section {
 
 extern "C" {
 
-int phsh_b200_split_phasout(const char* phasout, const char* const* names, int n_names, char* written,
-                            int written_cap) {
+static int split_phasout_impl(const char* phasout, const char* const* names, int n_names, char* written,
+                             int written_cap) {
     if (!phasout) {
         set_error("NULL path");
         return PHSH_B200_EINVAL;
@@ -158,8 +160,8 @@ int phsh_b200_split_phasout(const char* phasout, const char* const* names, int n
     return static_cast<int>(idx.size());
 }
 
-int phsh_b200_conphas_files(const char* const* inputs, int n_inputs, const char* output_file, const char* format,
-                            int lmax, const phsh_b200_conphas_opts* opts) {
+static int conphas_files_impl(const char* const* inputs, int n_inputs, const char* output_file, const char* format,
+                              int lmax, const phsh_b200_conphas_opts* opts) {
     if (!inputs || n_inputs < 0 || !output_file || lmax < 0) {
         set_error("bad arguments");
         return PHSH_B200_EINVAL;
@@ -183,6 +185,10 @@ int phsh_b200_conphas_files(const char* const* inputs, int n_inputs, const char*
             !to_double(h[3], &dl) || h[2].find_first_not_of("+-0123456789") != std::string::npos ||
             h[3].find_first_not_of("+-0123456789") != std::string::npos) {
             set_error("'%s': bad header line (initial energy, step, n_phases, lmf)", inputs[i]);
+            return PHSH_B200_EIO;
+        }
+        if (!(dn >= -2.0e9 && dn <= 2.0e9) || !(dl >= -1.0 && dl <= 1.0e4)) {
+            set_error("'%s': header values out of range (n_phases=%g, lmf=%g)", inputs[i], dn, dl);
             return PHSH_B200_EIO;
         }
         Section& S = secs[i];
@@ -351,6 +357,26 @@ int phsh_b200_conphas_files(const char* const* inputs, int n_inputs, const char*
     }
     fclose(f);
     return 0;
+}
+
+#define PHSH_GUARDED(call)                                                \
+    try {                                                                 \
+        return call;                                                      \
+    } catch (const std::bad_alloc&) {                                     \
+        set_error("out of host memory while processing the input file");  \
+        return PHSH_B200_ENOMEM;                                          \
+    } catch (const std::exception& e) {                                   \
+        set_error("unexpected error: %s", e.what());                      \
+        return PHSH_B200_EINVAL;                                          \
+    }
+
+int phsh_b200_split_phasout(const char* phasout, const char* const* names, int n_names, char* written,
+                            int written_cap) {
+    PHSH_GUARDED(split_phasout_impl(phasout, names, n_names, written, written_cap))
+}
+int phsh_b200_conphas_files(const char* const* inputs, int n_inputs, const char* output_file, const char* format,
+                            int lmax, const phsh_b200_conphas_opts* opts) {
+    PHSH_GUARDED(conphas_files_impl(inputs, n_inputs, output_file, format, lmax, opts))
 }
 
 }  // extern "C"

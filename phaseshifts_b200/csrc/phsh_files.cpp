@@ -13,6 +13,8 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <new>
+#include <stdexcept>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -177,7 +179,8 @@ void rel_energies(RelBlock& b, int cap, bool asbuilt) {
         DE = 0.025;
         UE = 1.0;
     }
-    int N = static_cast<int>((UE - ES) / DE + 0.5);
+    const double nd = (UE - ES) / DE + 0.5;
+    int N = (nd > -2.0e9 && nd < 2.0e9) ? static_cast<int>(nd) : (nd > 0 ? 2000000000 : 0);  // int() like the Fortran
     N = N + 1;
     b.n_header = N;
     b.es_h = ES;
@@ -222,7 +225,7 @@ phsh_b200_file_opts default_opts(const phsh_b200_file_opts* o) {
 
 extern "C" {
 
-int phsh_b200_rel_file(const char* mufftin, const char* phasout, const char* dataph, const char* inpdat,
+static int phsh_b200_rel_file_impl(const char* mufftin, const char* phasout, const char* dataph, const char* inpdat,
                        const phsh_b200_file_opts* opts_in) {
     const phsh_b200_file_opts o = default_opts(opts_in);
     if (!mufftin || !phasout || !dataph || !inpdat) {
@@ -285,6 +288,13 @@ int phsh_b200_rel_file(const char* mufftin, const char* phasout, const char* dat
         if (b.jri < 7 || b.lsm < 0 || b.lsm > 63) {
             set_error("block '%s': JRI=%d / LSM=%d not supported (need JRI>=7, 0<=LSM<=63)", b.name.c_str(), b.jri, b.lsm);
             return PHSH_B200_EINVAL;
+        }
+        {
+            const double de = b.de > 0.0 ? b.de : 0.025, span = b.de > 0.0 ? b.ue - b.es : 1.5;
+            if (!(o.max_energies > 0) && !(span / de < 1.0e7)) {
+                set_error("block '%s': %g energies requested with the 250-energy cap lifted", b.name.c_str(), span / de);
+                return PHSH_B200_EINVAL;
+            }
         }
         rel_energies(b, o.max_energies, asbuilt);
         blocks.push_back(std::move(b));
@@ -367,7 +377,7 @@ int phsh_b200_rel_file(const char* mufftin, const char* phasout, const char* dat
     return 0;
 }
 
-int phsh_b200_cav_file(const char* mufftin, const char* phasout, const char* dataph, const char* zph,
+static int phsh_b200_cav_file_impl(const char* mufftin, const char* phasout, const char* dataph, const char* zph,
                        const phsh_b200_file_opts* opts_in) {
     const phsh_b200_file_opts o = default_opts(opts_in);
     if (!mufftin || !phasout || !dataph || !zph) {
@@ -534,7 +544,7 @@ static bool parse_namelist(const std::string& text, const char* name, std::map<s
     return true;
 }
 
-int phsh_b200_wil_file(const char* mufftin, const char* phasout, const char* dataph, const char* zph,
+static int phsh_b200_wil_file_impl(const char* mufftin, const char* phasout, const char* dataph, const char* zph,
                        const phsh_b200_file_opts* opts_in) {
     const phsh_b200_file_opts o = default_opts(opts_in);
     if (!mufftin || !phasout || !dataph || !zph) {
@@ -665,6 +675,31 @@ int phsh_b200_wil_file(const char* mufftin, const char* phasout, const char* dat
             }
     }
     return 0;
+}
+
+// exception barrier: nothing may propagate through the C ABI
+#define PHSH_GUARDED(call)                                                \
+    try {                                                                 \
+        return call;                                                      \
+    } catch (const std::bad_alloc&) {                                     \
+        set_error("out of host memory while processing the input file");  \
+        return PHSH_B200_ENOMEM;                                          \
+    } catch (const std::exception& e) {                                   \
+        set_error("unexpected error: %s", e.what());                      \
+        return PHSH_B200_EINVAL;                                          \
+    }
+
+int phsh_b200_rel_file(const char* mufftin, const char* phasout, const char* dataph, const char* inpdat,
+                       const phsh_b200_file_opts* opts) {
+    PHSH_GUARDED(phsh_b200_rel_file_impl(mufftin, phasout, dataph, inpdat, opts))
+}
+int phsh_b200_cav_file(const char* mufftin, const char* phasout, const char* dataph, const char* zph,
+                       const phsh_b200_file_opts* opts) {
+    PHSH_GUARDED(phsh_b200_cav_file_impl(mufftin, phasout, dataph, zph, opts))
+}
+int phsh_b200_wil_file(const char* mufftin, const char* phasout, const char* dataph, const char* zph,
+                       const phsh_b200_file_opts* opts) {
+    PHSH_GUARDED(phsh_b200_wil_file_impl(mufftin, phasout, dataph, zph, opts))
 }
 
 }  // extern "C"
