@@ -100,7 +100,12 @@ def test_cav_wil_phasout_mutations(tmp_path, seed, mode, which):
     else:
         c = Conphas(input_files=[str(p)], output_file=str(tmp_path / "o"), formatting="curve", lmax=4)
         _call(c.calculate)
-        _call(Conphas.split_phasout, str(p), [str(tmp_path / "s.ph")])
+        cwd = os.getcwd()
+        os.chdir(tmp_path)  # sections beyond the given names are written under guessed names in the cwd
+        try:
+            _call(Conphas.split_phasout, str(p), [str(tmp_path / "s.ph")])
+        finally:
+            os.chdir(cwd)
 
 
 def test_absurd_headers_are_rejected_not_allocated(tmp_path):
