@@ -109,6 +109,8 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
                                 const double* e_l, long e_stride, int NE, const RelConsts& c, int jpad, double* raw,
                                 unsigned long long* counters, cudaStream_t st) {
     const int L1 = c.lsm + 1;
+    // launch-shape knobs kept for experiments (profiles/README.md lists what they measured); defaults are the
+    // shipped configuration
     static const int env_block = getenv("PHSH_B200_BLOCK") ? atoi(getenv("PHSH_B200_BLOCK")) : 0;
     static const int env_lgroups = getenv("PHSH_B200_LGROUPS") ? atoi(getenv("PHSH_B200_LGROUPS")) : 0;
     static const int env_pack = getenv("PHSH_B200_PACK") ? atoi(getenv("PHSH_B200_PACK")) : 1;
@@ -126,13 +128,8 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
     while (ctas * lgroups < target && lgroups < L1) ++lgroups;
     if (env_lgroups > 0) lgroups = std::min(std::max(lgroups, env_lgroups), L1);
     const size_t smem = static_cast<size_t>(kmax + 1) * jpad * sizeof(double) + 16;
-    // resident CTAs per SM the integrator is compiled for (register cap 65536/(128*MINB)); 6 measured fastest
-    static const int minb = getenv("PHSH_B200_MINB") ? atoi(getenv("PHSH_B200_MINB")) : 6;
-    auto kern = minb == 4   ? rel_integrate_kernel<FAST, Real, 4>
-                : minb == 5 ? rel_integrate_kernel<FAST, Real, 5>
-                : minb == 7 ? rel_integrate_kernel<FAST, Real, 7>
-                : minb == 8 ? rel_integrate_kernel<FAST, Real, 8>
-                            : rel_integrate_kernel<FAST, Real, 6>;
+    // compiled for kRelMinBlocks = 6 resident CTAs per SM (80 registers): fastest of 4..8 measured on C4
+    auto kern = rel_integrate_kernel<FAST, Real, kRelMinBlocks>;
     if (smem > 48 * 1024) PHSH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long grid = ctas * lgroups;
     if (grid > 0x7fffffffL) {

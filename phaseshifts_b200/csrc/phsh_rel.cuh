@@ -322,6 +322,8 @@ __device__ __forceinline__ Real sbfit_match(const Bessel<Real>& b, double T, int
 // kernel A: integrate + match.  raw[((p*L1 + l)*NE + ie)*2 + {0: JFD (kappa=l), 1: JFU (kappa=-l-1)}]
 // grid.x = P * lgroups * chunks (p major), block = 32..128 threads, dyn smem = 2*jpad doubles + 16 B
 // =================================================================================================
+constexpr int kRelMinBlocks = 6;  // resident CTAs per SM the integrator is compiled for (<= 80 registers)
+
 template <bool FAST, class Real, int MINB>
 __global__ void __launch_bounds__(128, MINB)
     rel_integrate_kernel(const double* __restrict__ pot, long pot_stride, const int* __restrict__ jri_arr,
