@@ -116,15 +116,17 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
     static const int env_pack = getenv("PHSH_B200_PACK") ? atoi(getenv("PHSH_B200_PACK")) : 1;
     int block = NE >= 128 ? 128 : ((NE + 31) / 32) * 32;
     if (env_block == 32 || env_block == 64 || env_block == 128) block = std::min(block, env_block);
-    // Packed lanes (a CTA may straddle potentials) when each potential still fills at least half a CTA, so that
-    // at most 3 potential tables are staged per CTA; otherwise every potential gets its own CTAs.
-    const bool packed = env_pack && NE >= 64 && P > 1;
+    // Packed lanes (a CTA may straddle potentials) as long as a CTA never needs more than 4 potential tables;
+    // otherwise (very short energy axes) every potential gets its own CTAs.
+    const int kpack = (block - 2) / std::max(NE, 1) + 2;
+    const bool packed = env_pack && P > 1 && kpack <= 4;
     const int lane_stride = packed ? NE : ((NE + block - 1) / block) * block;
-    const int kmax = packed ? (block - 2) / NE + 2 : 1;
+    const int kmax = packed ? kpack : 1;
     const long ctas = (static_cast<long>(P) * lane_stride + block - 1) / block;
-    // enough CTAs to fill 148 SMs several times over; otherwise split the l range across CTAs
+    // At least ~8 waves of CTAs (148 SMs x 6 resident), so that the partially filled last wave costs little;
+    // smaller batches split the l range across CTAs (costly high-l groups first) to get there.
     int lgroups = 1;
-    const long target = 148L * 8;
+    const long target = 148L * kRelMinBlocks * 8;
     while (ctas * lgroups < target && lgroups < L1) ++lgroups;
     if (env_lgroups > 0) lgroups = std::min(std::max(lgroups, env_lgroups), L1);
     const size_t smem = static_cast<size_t>(kmax + 1) * jpad * sizeof(double) + 16;
@@ -165,7 +167,7 @@ static int rel_check(long pot_stride, int P, int NE, const phsh_b200_rel_opts* o
         set_error("bad radial grid xs=%g dx=%g", o->xs, o->dx);
         return PHSH_B200_EINVAL;
     }
-    if (static_cast<size_t>(4 * (pot_stride + 2)) * sizeof(double) + 16 > 200 * 1024) {
+    if (static_cast<size_t>(5 * (pot_stride + 2)) * sizeof(double) + 16 > 200 * 1024) {
         set_error("pot_stride=%ld does not fit the shared-memory staging buffer", pot_stride);
         return PHSH_B200_EINVAL;
     }
