@@ -72,3 +72,34 @@ def test_device_tensor_path_equals_host_path():
     dev = api.phsh_rel_batch(torch.from_numpy(pot).cuda(), jri, g["e_l"], 12, energies_l0=g["e_l0"])
     torch.cuda.synchronize()
     assert np.array_equal(dev.cpu().numpy(), h)
+
+
+def test_two_stage_entry_points_equal_the_fused_call(oracle):
+    """phsh_b200_rel_integrate_device + phsh_b200_rel_energy_axis_device == phsh_b200_rel_batch_device."""
+    import ctypes as C
+    import torch
+    from phaseshifts_b200 import api, _lib, workloads
+    w = workloads.c4_sweep(P=5, ne=130, lmax=7)
+    g = w["grid"]
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    pot = torch.from_numpy(w["pot"]).to(dev)
+    jri = torch.from_numpy(w["jri"]).to(dev)
+    e0, e1 = torch.from_numpy(g["e_l0"]).to(dev), torch.from_numpy(g["e_l"]).to(dev)
+    raw = torch.empty((5, 8, 130, 2), dtype=torch.float64, device=dev)
+    out = torch.empty((5, 130, 8), dtype=torch.float64, device=dev)
+    opts = _lib.RelOpts(api.XS_DEFAULT, api.DX_DEFAULT, 7, _lib.UNWRAP)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(lib.phsh_b200_rel_integrate_device(p(pot), pot.shape[1], p(jri), 5, p(e0), p(e1), 0, 130, C.byref(opts),
+                                                  p(raw), None, st))
+    _lib.check(lib.phsh_b200_rel_energy_axis_device(p(raw), 5, 130, C.byref(opts), p(out), st))
+    fused, kap = api.phsh_rel_batch(pot, jri, e1, 7, energies_l0=e0, unwrap=True, per_kappa=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, fused) and torch.equal(raw, kap)
+    ref = oracle.rel_batch(w["pot"], w["jri"], g["e_l0"], g["e_l"], lsm=7, per_kappa=True)
+    assert np.abs(raw.cpu().numpy().transpose(0, 2, 1, 3) - ref["jfk"]).max() <= TOL
+    # misaligned potentials are refused (TMA bulk copies need 16-byte aligned rows)
+    bad = torch.empty(5 * 326 + 1, dtype=torch.float64, device=dev)[1:].view(5, 326)
+    rc = lib.phsh_b200_rel_integrate_device(p(bad), 326, p(jri), 5, p(e0), p(e1), 0, 130, C.byref(opts), p(raw), None, st)
+    assert rc == _lib.EINVAL and b"aligned" in lib.phsh_b200_last_error()
