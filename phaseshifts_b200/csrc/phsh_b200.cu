@@ -128,10 +128,18 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
     int lgroups = 1;
     const long target = 148L * kRelMinBlocks * 8;
     while (ctas * lgroups < target && lgroups < L1) ++lgroups;
-    if (env_lgroups > 0) lgroups = std::min(std::max(lgroups, env_lgroups), L1);
+    // still short of CTAs with one l per CTA: split the two kappa of an l as well (KSPLIT kernel)
+    const int nitems = 2 * L1 - 1;  // kappa items per lane
+    bool ksplit = false;
+    if (ctas * lgroups < target && lgroups == L1 && L1 > 1) {
+        ksplit = true;
+        while (ctas * lgroups < target && lgroups < nitems) ++lgroups;
+    }
+    if (env_lgroups > 0) lgroups = std::min(std::max(lgroups, env_lgroups), ksplit ? nitems : L1);
     const size_t smem = static_cast<size_t>(kmax + 1) * jpad * sizeof(double) + 16;
     // compiled for kRelMinBlocks = 6 resident CTAs per SM (80 registers): fastest of 4..8 measured on C4
-    auto kern = rel_integrate_kernel<FAST, Real, kRelMinBlocks>;
+    auto kern = ksplit ? rel_integrate_kernel<FAST, Real, kRelMinBlocks, true>
+                       : rel_integrate_kernel<FAST, Real, kRelMinBlocks, false>;
     if (smem > 48 * 1024) PHSH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long grid = ctas * lgroups;
     if (grid > 0x7fffffffL) {

@@ -324,7 +324,10 @@ __device__ __forceinline__ Real sbfit_match(const Bessel<Real>& b, double T, int
 // =================================================================================================
 constexpr int kRelMinBlocks = 6;  // resident CTAs per SM the integrator is compiled for (<= 80 registers)
 
-template <bool FAST, class Real, int MINB>
+// KSPLIT=false: the CTAs of a lane tile share the l range (both kappa of an l stay in one thread) -- large batches.
+// KSPLIT=true : they share the list of 2*L1-1 kappa items, so the two kappa of one l may run in different CTAs --
+//               small, latency-bound batches (up to twice as many CTAs).
+template <bool FAST, class Real, int MINB, bool KSPLIT>
 __global__ void __launch_bounds__(128, MINB)
     rel_integrate_kernel(const double* __restrict__ pot, long pot_stride, const int* __restrict__ jri_arr,
                          const double* __restrict__ e_l0, const double* __restrict__ e_l, long e_stride, int NE, int P,
@@ -345,10 +348,20 @@ __global__ void __launch_bounds__(128, MINB)
     const int p_first = static_cast<int>(g0 / lane_stride);
     const int p_last = static_cast<int>(min((g0 + blockDim.x - 1) / lane_stride, static_cast<long>(P - 1)));
     const int npot = min(p_last - p_first + 1, kmax);
-    const int lper = (L1 + lgroups - 1) / lgroups;
-    // costly (high-l) groups are scheduled first
-    const int l_hi = L1 - 1 - lg * lper;
-    const int l_lo = max(l_hi - lper + 1, 0);
+    // The work of a lane is a list of 2*L1-1 kappa items: t=0 -> (l=0, kappa=-1); t=2l-1 -> (l, kappa=-l-1);
+    // t=2l -> (l, kappa=l).  `lgroups` CTAs share the list, costly (high-|kappa|) groups scheduled first.
+    int t_hi, t_lo;
+    if (KSPLIT) {
+        const int nitems = 2 * L1 - 1;
+        const int tper = (nitems + lgroups - 1) / lgroups;
+        t_hi = nitems - 1 - lg * tper;
+        t_lo = max(t_hi - tper + 1, 0);
+    } else {
+        const int lper = (L1 + lgroups - 1) / lgroups;
+        const int l_hi = L1 - 1 - lg * lper, l_lo = max(l_hi - lper + 1, 0);
+        t_hi = 2 * l_hi;
+        t_lo = l_lo == 0 ? 0 : 2 * l_lo - 1;
+    }
 
     // A device-resident jri cannot be validated by the host without a sync: out-of-range entries (the Fortran
     // stops at such a block, libphsh.f:4609) produce NaN phases instead of out-of-bounds shared-memory accesses.
@@ -407,19 +420,29 @@ __global__ void __launch_bounds__(128, MINB)
     const double c4pi = static_cast<double>(12.5663706f);
     unsigned steps = 0, evals = 0, calls = 0;
 
+    double* rawd = raw;
     if (active && !valid) {
-        for (int l = l_hi; l >= l_lo; --l)
-            reinterpret_cast<double2*>(raw)[(static_cast<size_t>(p) * L1 + l) * NE + ie] = make_double2(nan(""), nan(""));
+        for (int t = t_hi; t >= t_lo; --t) {
+            const int l = (t + 1) >> 1;
+            double* q = rawd + ((static_cast<size_t>(p) * L1 + l) * NE + ie) * 2;
+            if (t == 0) q[0] = q[1] = nan("");
+            else q[t & 1] = nan("");
+        }
     } else if (active) {
         const double R = r_s[jri - 1];
-        for (int l = l_hi; l >= l_lo; --l) {
+        const int l_top = (t_hi + 1) >> 1, l_bot = (t_lo + 1) >> 1;
+        for (int l = l_top; l >= l_bot; --l) {
             const double E = (l == 0) ? E0 : E1;
-            // kappa = -(l+1) first, then kappa = l.  One copy of the integrator in the instruction stream: with
-            // two inlined copies the unrolled Milne phases overflow the instruction cache (measured 287 vs 220 ms).
+            // which of this l's kappa items fall into the CTA's range: s=0 -> kappa=-(l+1) (item 2l-1, or 0 for l=0),
+            // s=1 -> kappa=l (item 2l)
+            const int t_u = l == 0 ? 0 : 2 * l - 1, t_d = 2 * l;
+            const bool do_u = !KSPLIT || (t_u >= t_lo && t_u <= t_hi);
+            const bool do_d = l > 0 && (!KSPLIT || (t_d >= t_lo && t_d <= t_hi));
+            // One copy of the integrator in the instruction stream: with two inlined copies the unrolled Milne
+            // phases overflow the instruction cache (measured 287 vs 220 ms).
             double dlu = 0.0, dld = 0.0;
-            const int nk = l > 0 ? 2 : 1;
 #pragma unroll 1
-            for (int s = 0; s < nk; ++s) {
+            for (int s = do_u ? 0 : 1; s < (do_d ? 2 : 1); ++s) {
                 const double v = dlgkap_dev<FAST>(pot_l, r_s, jri, E, s == 0 ? -(l + 1) : l, c, steps, evals) / c4pi;
                 ++calls;
                 if (s == 0)
@@ -427,13 +450,15 @@ __global__ void __launch_bounds__(128, MINB)
                 else
                     dld = v;
             }
+            // j_l, n_l once per (E, l), shared by the two kappa (phsh2.f:1044-1059)
             const Bessel<Real> b = sbfit_bessel<Real>(E, R, l, asbuilt);
-            const Real JFU = sbfit_match<Real>(b, dlu, l);
-            const Real JFD = l > 0 ? sbfit_match<Real>(b, dld, l) : JFU;
-            double2 o;
-            o.x = static_cast<double>(JFD);
-            o.y = static_cast<double>(JFU);
-            reinterpret_cast<double2*>(raw)[(static_cast<size_t>(p) * L1 + l) * NE + ie] = o;
+            double* q = rawd + ((static_cast<size_t>(p) * L1 + l) * NE + ie) * 2;
+            if (do_u) {
+                const double jfu = static_cast<double>(sbfit_match<Real>(b, dlu, l));
+                q[1] = jfu;               // .y = JFU (kappa = -l-1)
+                if (l == 0) q[0] = jfu;   // l = 0 has the single kappa = -1
+            }
+            if (do_d) q[0] = static_cast<double>(sbfit_match<Real>(b, dld, l));  // .x = JFD (kappa = l)
         }
     }
     if (counters != nullptr) {
