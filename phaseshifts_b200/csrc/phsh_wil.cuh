@@ -147,20 +147,19 @@ __device__ __forceinline__ void hamming_step(double (&yP)[4], double (&yQ)[4], d
     using M = RMath<double>;
     constexpr int ip1 = PH, im2 = (PH + 1) % 4, im1 = (PH + 2) % 4, ip0 = (PH + 3) % 4;
     const double cmod = static_cast<double>(0.925619835f), cfin = static_cast<double>(.743801653E-1f);
-    fP[im2] = M::add(yP[ip1], div_by_0p75(M::sub(M::mul(2.0, M::add(fP[ip0], fP[im2])), fP[im1])));
+    // products by 2.0 and 0.125 are exact, so fusing them into the following add/sub rounds identically
+    fP[im2] = M::add(yP[ip1], div_by_0p75(__fma_rn(2.0, M::add(fP[ip0], fP[im2]), -fP[im1])));
     yP[ip1] = M::sub(fP[im2], M::mul(cmod, eP));
-    fQ[im2] = M::add(yQ[ip1], div_by_0p75(M::sub(M::mul(2.0, M::add(fQ[ip0], fQ[im2])), fQ[im1])));
+    fQ[im2] = M::add(yQ[ip1], div_by_0p75(__fma_rn(2.0, M::add(fQ[ip0], fQ[im2]), -fQ[im1])));
     yQ[ip1] = M::sub(fQ[im2], M::mul(cmod, eQ));
     fP[ip1] = M::mul(M::add(M::mul(FLP1, yP[ip1]), M::mul(Ri, yQ[ip1])), T1);
     fQ[ip1] = M::mul(M::sub(M::mul(VME, yP[ip1]), M::mul(FLP1, yQ[ip1])), T1);
-    yP[ip1] = M::add(yP[ip0], M::mul(M::add(M::sub(yP[ip0], yP[im2]),
-                                            M::mul(3.0, M::sub(M::add(fP[ip1], M::mul(2.0, fP[ip0])), fP[im1]))),
-                                     0.125));
+    yP[ip1] = __fma_rn(M::add(M::sub(yP[ip0], yP[im2]), M::mul(3.0, M::sub(__fma_rn(2.0, fP[ip0], fP[ip1]), fP[im1]))),
+                       0.125, yP[ip0]);
     eP = M::sub(fP[im2], yP[ip1]);
     yP[ip1] = M::add(yP[ip1], M::mul(cfin, eP));
-    yQ[ip1] = M::add(yQ[ip0], M::mul(M::add(M::sub(yQ[ip0], yQ[im2]),
-                                            M::mul(3.0, M::sub(M::add(fQ[ip1], M::mul(2.0, fQ[ip0])), fQ[im1]))),
-                                     0.125));
+    yQ[ip1] = __fma_rn(M::add(M::sub(yQ[ip0], yQ[im2]), M::mul(3.0, M::sub(__fma_rn(2.0, fQ[ip0], fQ[ip1]), fQ[im1]))),
+                       0.125, yQ[ip0]);
     eQ = M::sub(fQ[im2], yQ[ip1]);
     yQ[ip1] = M::add(yQ[ip1], M::mul(cfin, eQ));
     fP[ip1] = M::mul(M::add(M::mul(FLP1, yP[ip1]), M::mul(Ri, yQ[ip1])), T1);
