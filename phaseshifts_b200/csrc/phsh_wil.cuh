@@ -115,8 +115,9 @@ __device__ inline double f45_dev(int L, double X) {
 // Outside the range where no intermediate over/underflows the general division is used.
 // (Checked against __ddiv_rn on random and edge-case inputs by phsh_b200_selftest_div075.)
 __device__ __forceinline__ double div_by_0p75(double x) {
-    const double ax = fabs(x);
-    if (!(ax > 1.0e-280 && ax < 1.0e+300)) return __ddiv_rn(x, 0.75);
+    // exponent window [2^-930, 2^+996] checked on the integer pipe (also rejects 0/denormal, Inf and NaN)
+    const unsigned e = (static_cast<unsigned>(__double2hiint(x)) >> 20) & 0x7ffu;
+    if (e - 93u > 1926u) return __ddiv_rn(x, 0.75);
     const double c = 1.3333333333333333;  // RN(4/3) = 0x3FF5555555555555
     const double q0 = __dmul_rn(x, c);
     const double r = __fma_rn(-0.75, q0, x);
