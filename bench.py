@@ -321,6 +321,18 @@ def main():
         ref = np.stack([orc.conphas(x) for x in r["jf"]])
         parity = float(np.abs(out_np[:n_pot] - ref).max())
 
+    # the same kernel seen against the HBM roofline (measured copy bandwidth of this pool's B200s): far from it
+    hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except (OSError, KeyError, ValueError):
+        pass
+    alg_bytes = pot_d.numel() * 8.0 + raw_d.numel() * 8.0
+    hbm_view = {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": alg_bytes}
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -339,6 +351,7 @@ def main():
                      "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum; algorithmic: "
                                      "%.3g in + %.3g per-kappa scratch out)" % (pot_d.numel() * 8.0, raw_d.numel() * 8.0),
                      "ncu_fp64_pipe_pct_of_peak_sustained_active": ncu_pipe,
+                     "hbm_view": hbm_view,
                      "kernel": "rel_integrate_kernel", "kernel_ms": kernel_ms,
                      "flops_per_launch": flops_per_launch,
                      "corrector_evals_per_step": float(c[2]) / max(float(c[1]), 1.0),
