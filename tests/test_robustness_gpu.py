@@ -126,3 +126,20 @@ def test_single_process_multi_device_sharding(oracle):
     ref = oracle.rel_batch(w["pot"], w["jri"], g["e_l0"], g["e_l"], lsm=6)["jf"]
     ref = np.stack([oracle.conphas(x) for x in ref])
     assert np.abs(got - ref).max() <= TOL
+
+
+def test_very_fine_radial_grid_uses_opt_in_shared_memory(oracle):
+    """dx = 1/256 -> ~2700 radial points per potential: the staging buffers exceed the 48 KB default and the
+    oracle leaves its stack arrays for the heap; results must still agree bit for bit in the integration."""
+    from phaseshifts_b200 import api, workloads
+    dx, xs = 1.0 / 256.0, -9.03065133
+    J = 2 * ((int(1 + round((np.log(3.0) - xs) / dx)) + 2) // 2)
+    r = np.exp(xs + np.arange(J) * dx)
+    pot = np.stack([workloads.moliere_rv(z, r) for z in (29, 79)])
+    jri = np.array([int(1 + round((np.log(rm) - xs) / dx)) for rm in (2.4, 2.9)], dtype=np.int32)
+    assert jri.max() > 2600
+    e = np.linspace(0.5, 40.0, 70)
+    got, cnt = api.phsh_rel_batch(pot, jri, e, 6, dx=dx, counters=True)
+    ref = oracle.rel_batch(pot, jri, e, lsm=6, dx=dx)
+    assert np.abs(got - ref["jf"]).max() <= TOL
+    assert (cnt["milne_steps"], cnt["corr_evals"]) == (ref["milne_steps"], ref["corr_evals"])
