@@ -339,7 +339,8 @@ def main():
         return
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "units_per_step": world * units_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "phaseshifts_b200.api.phsh_rel_batch(host arrays) -> phsh_b200_rel_batch_host",
