@@ -41,7 +41,7 @@ def nbytes(k):
 
 
 rd, wr = nbytes("dram__bytes_read.sum"), nbytes("dram__bytes_write.sum")
-cap = {"kernel": "rel_integrate_kernel<false,double,6>", "workload": "C4: 4096 potentials x 1000 energies x lmax 15",
+cap = {"kernel": "rel_integrate_kernel<false,double,6,false>", "workload": "C4: 4096 potentials x 1000 energies x lmax 15",
        "dram_bytes_read": rd, "dram_bytes_write": wr, "traffic_bytes_per_launch": rd + wr,
        "gpu_time_ms_under_ncu": get("gpu__time_duration.sum")[0],
        "fp64_pipe_pct_of_peak_sustained_active": get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")[0],

@@ -1,5 +1,8 @@
-# Regenerates every artefact under profiles/ for the current tree (1 GPU).  Usage: gpurun -- bash scripts/gpu_profile_all.sh
+# Regenerates every artefact under profiles/ for the current tree (1 GPU), one ncu pass per call.
+# Usage: gpurun -- bash scripts/gpu_profile_all.sh 1   (tests, bench lines, launch list)
+#        gpurun -- bash scripts/gpu_profile_all.sh 2   (ncu --set full capture of the dominant kernel)
 set -x
+if [ "${1:-1}" = 1 ]; then
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.txt; cat gpurun_out/pytest_gpu.txt
 python bench.py --steps 5 --warmup 3 2> gpurun_out/bench_err.log > gpurun_out/final_bench_n1.json
 python bench.py --impl reference --steps 2 --warmup 1 2>> gpurun_out/bench_err.log > gpurun_out/final_bench_n1_reference.json
@@ -7,8 +10,10 @@ python scripts/bench_paths.py > gpurun_out/final_secondary.jsonl 2>> gpurun_out/
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final_launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+cut -c1-200 gpurun_out/final_bench_n1.json
+else
 CMD2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD2 > gpurun_out/ncu_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:rel_integrate -s 3 -c 1 -o gpurun_out/final_prof_rel $CMD2 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log | cut -c1-200
-cut -c1-200 gpurun_out/final_bench_n1.json
+fi
