@@ -40,6 +40,20 @@ class ConphasOpts(C.Structure):
                 ("device", C.c_int), ("unwrap_all_inputs", C.c_int)]
 
 
+class CavpotBatch(C.Structure):
+    _fields_ = [("n_struct", C.c_int), ("n_types", C.c_int), ("n_atoms", C.c_int), ("max_types", C.c_int),
+                ("max_atoms", C.c_int), ("type_off", C.c_void_p), ("atom_off", C.c_void_p), ("rc", C.c_void_p),
+                ("nrr", C.c_void_p), ("z", C.c_void_p), ("zc", C.c_void_p), ("rmt", C.c_void_p), ("dens", C.c_void_p),
+                ("rk", C.c_void_p), ("n_dens", C.c_int), ("rho", C.c_void_p), ("nx", C.c_void_p), ("alpha", C.c_void_p),
+                ("nh", C.c_void_p), ("slab", C.c_void_p), ("esht", C.c_void_p), ("nform", C.c_void_p)]
+
+
+class CavpotResult(C.Structure):
+    _fields_ = [("mtz", C.c_void_p), ("npts", C.c_void_p), ("pot", C.c_void_p), ("pot_stride", C.c_long),
+                ("vh", C.c_void_p), ("vs", C.c_void_p), ("vmad", C.c_void_p), ("shell_ad", C.c_void_p),
+                ("shell_na", C.c_void_p), ("shell_ia", C.c_void_p), ("ncon", C.c_void_p), ("stats", C.c_void_p)]
+
+
 _dp = C.c_void_p  # raw addresses (host numpy or device tensor data_ptr)
 _SIGNATURES = {
     "phsh_b200_last_error": (C.c_char_p, []),
@@ -68,6 +82,12 @@ _SIGNATURES = {
     "phsh_b200_split_phasout": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int]),
     "phsh_b200_conphas_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int,
                                           C.POINTER(ConphasOpts)]),
+    "phsh_b200_cavpot_batch_host": (C.c_int, [C.POINTER(CavpotBatch), C.POINTER(CavpotResult), C.c_int, C.c_int]),
+    "phsh_b200_cavpot_batch_device": (C.c_int, [C.POINTER(CavpotBatch), C.POINTER(CavpotResult), C.c_int, C.c_void_p]),
+    "phsh_b200_cavpot_rela_density": (C.c_int, [C.c_double, C.c_double, C.c_int, _dp, C.c_int, _dp, C.POINTER(C.c_int),
+                                                C.c_int]),
+    "phsh_b200_cavpot_file": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
+                                        C.POINTER(FileOpts), C.POINTER(C.c_double)]),
     "phsh_b200_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "phsh_b200_selftest_div075": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),
 }

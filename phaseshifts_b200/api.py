@@ -303,3 +303,95 @@ def phsh_cav_file(mufftin, phasout, dataph, zph, *, asbuilt=False, conphas_heade
 def phsh_wil_file(mufftin, phasout, dataph, zph, *, device=0):
     """``libphsh.phsh_wil(mufftin, phasout, dataph, zph)`` (libphsh.f:3893; original control flow phsh2.f:314-433)."""
     _file_call(_lib.load().phsh_b200_wil_file, mufftin, phasout, dataph, zph, 0, 250, 340, device)
+
+
+# ---- muffin-tin potential step (CAVPOT) ---------------------------------------------------------------------
+def cavpot_rela_density(rmin, rmax, rs, iprint=0, device=0):
+    """``RELA`` (``libphsh.f:3460-3507``): a charge density tabulated on the atomic program's logarithmic mesh
+    ``rmin*(rmax/rmin)**(i/nr)`` -> (rho[250] on Loucks' mesh, NX).  The interpolation (``CHGRID``) runs on the GPU."""
+    rs = _np64(rs).reshape(-1)
+    rho = np.zeros(250, dtype=np.float64)
+    nx = C.c_int(0)
+    _lib.check(_lib.load().phsh_b200_cavpot_rela_density(float(rmin), float(rmax), int(rs.size), _ptr(rs), int(iprint),
+                                                        _ptr(rho), C.byref(nx), int(device)))
+    return rho, int(nx.value)
+
+
+def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
+    """The muffin-tin potential step of ``libphsh.cavpot`` (``libphsh.f:2070-2557``) for a batch of structures.
+
+    ``structures``: sequence of dicts with ``spa`` (lattice constant, bohr), ``rc`` [3][3] (axis j = ``rc[j]``, in units of
+    ``spa``), ``nrr`` [nr], ``z`` [nr], ``zc`` [nr], ``rmt`` [nr], ``rk`` [n_atoms][3] (units of ``spa``, listed type by type),
+    ``dens`` [nr] (row of ``rho`` for each atom type), ``alpha``, ``nh``, ``nform`` and optionally ``slab`` / ``esht``.
+    ``rho`` [n_dens][250], ``nx`` [n_dens]: the atomic charge densities on Loucks' mesh (``cavpot_rela_density``).
+
+    Returns a dict: ``mtz`` [S] (VHAR+VEX, what ``cavpot`` returns for a bulk run), ``vhar``, ``vex`` [S], ``npts`` [T],
+    ``pot`` [T][421], ``type_off`` [S+1]; with ``diagnostics`` also ``vh``, ``vs``, ``vmad`` [T][250], the neighbour shells
+    ``shell_ad/na/ia`` [T][30], ``ncon`` [T] and ``stats`` [S][4] (NINT, NPOINT, JRWS, NH after doubling).
+    """
+    S = len(structures)
+    type_off = np.zeros(S + 1, dtype=np.int32)
+    atom_off = np.zeros(S + 1, dtype=np.int32)
+    rc, nrr, z, zc, rmt, dens, rk = [], [], [], [], [], [], []
+    alpha = np.zeros(S)
+    nh = np.zeros(S, dtype=np.int32)
+    slab = np.zeros(S, dtype=np.int32)
+    esht = np.zeros(S)
+    nform = np.zeros(S, dtype=np.int32)
+    for s, st in enumerate(structures):
+        spa = float(st["spa"])
+        n_r = np.asarray(st["nrr"], dtype=np.int32).reshape(-1)
+        pos = np.asarray(st["rk"], dtype=np.float64).reshape(-1, 3)
+        type_off[s + 1] = type_off[s] + n_r.size
+        atom_off[s + 1] = atom_off[s] + pos.shape[0]
+        rc.append(spa * np.asarray(st["rc"], dtype=np.float64).reshape(9))  # RC(I,J)=SPA*RC(I,J) (libphsh.f:2133-2137)
+        rk.append(spa * pos)
+        nrr.append(n_r)
+        z.append(np.asarray(st["z"], dtype=np.float64).reshape(-1))
+        zc.append(np.asarray(st["zc"], dtype=np.float64).reshape(-1))
+        rmt.append(np.asarray(st["rmt"], dtype=np.float64).reshape(-1))
+        dens.append(np.asarray(st["dens"], dtype=np.int32).reshape(-1))
+        alpha[s], nh[s], nform[s] = float(st["alpha"]), int(st["nh"]), int(st["nform"])
+        slab[s], esht[s] = int(st.get("slab", 0)), float(st.get("esht", 0.0))
+    T, A = int(type_off[-1]), int(atom_off[-1])
+    cat = lambda parts, dt: np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0), dtype=dt)
+    rc, rk = cat(rc, np.float64), cat([r.reshape(-1) for r in rk], np.float64)
+    nrr, z, zc, rmt, dens = cat(nrr, np.int32), cat(z, np.float64), cat(zc, np.float64), cat(rmt, np.float64), cat(dens, np.int32)
+    rho = np.ascontiguousarray(np.asarray(rho, dtype=np.float64).reshape(-1, 250))
+    nx = np.ascontiguousarray(np.asarray(nx, dtype=np.int32).reshape(-1))
+    for name, arr in (("z", z), ("zc", zc), ("rmt", rmt), ("dens", dens)):
+        if arr.size != T:
+            raise ValueError("%s has %d entries for %d atom types" % (name, arr.size, T))
+    b = _lib.CavpotBatch()
+    b.n_struct, b.n_types, b.n_atoms, b.max_types, b.max_atoms, b.n_dens = S, T, A, 0, 0, int(rho.shape[0])
+    keep = dict(type_off=type_off, atom_off=atom_off, rc=rc, nrr=nrr, z=z, zc=zc, rmt=rmt, dens=dens, rk=rk, rho=rho, nx=nx,
+                alpha=alpha, nh=nh, slab=slab, esht=esht, nform=nform)
+    for k, v in keep.items():
+        setattr(b, k, v.ctypes.data)
+    out = dict(mtz2=np.zeros((S, 2)), npts=np.zeros(T, dtype=np.int32), pot=np.zeros((T, 421)))
+    r = _lib.CavpotResult()
+    r.mtz, r.npts, r.pot, r.pot_stride = out["mtz2"].ctypes.data, out["npts"].ctypes.data, out["pot"].ctypes.data, 421
+    if diagnostics:
+        out.update(vh=np.zeros((T, 250)), vs=np.zeros((T, 250)), vmad=np.zeros((T, 250)), shell_ad=np.zeros((T, 30)),
+                   shell_na=np.zeros((T, 30), dtype=np.int32), shell_ia=np.zeros((T, 30), dtype=np.int32),
+                   ncon=np.zeros(T, dtype=np.int32), stats=np.zeros((S, 4), dtype=np.int32))
+        for k in ("vh", "vs", "vmad", "shell_ad", "shell_na", "shell_ia", "ncon", "stats"):
+            setattr(r, k, out[k].ctypes.data)
+    _lib.check(_lib.load().phsh_b200_cavpot_batch_host(C.byref(b), C.byref(r), 0, int(device)))
+    out["vhar"], out["vex"] = out["mtz2"][:, 0].copy(), out["mtz2"][:, 1].copy()
+    out["mtz"] = out["vhar"] + out["vex"]
+    out["type_off"] = type_off
+    del out["mtz2"]
+    return out
+
+
+def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file, *, real32=True,
+                device=0):
+    """``libphsh.cavpot`` with its seven arguments (``libphsh.f:2070-2071``); returns the muffin-tin zero of a bulk run."""
+    opts = _lib.FileOpts(REAL32 if real32 else 0, 0, 0, int(device))
+    mtz = C.c_double(0.0)
+    enc = lambda s: str(s).encode()
+    _lib.check(_lib.load().phsh_b200_cavpot_file(enc(mtz_string), int(slab_flag), enc(atomic_file), enc(cluster_file),
+                                                 enc(mufftin_file), enc(output_file), enc(info_file), C.byref(opts),
+                                                 C.byref(mtz)))
+    return float(mtz.value)

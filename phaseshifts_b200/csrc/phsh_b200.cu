@@ -11,6 +11,7 @@
 #include "phsh_rel.cuh"
 #include "phsh_cav.cuh"
 #include "phsh_wil.cuh"
+#include "phsh_cavpot.cuh"
 
 namespace phsh {
 
@@ -455,3 +456,4 @@ int phsh_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz_est) {
 }  // extern "C"
 
 #include "phsh_cav_wil_abi.inc"
+#include "phsh_cavpot_abi.inc"

@@ -702,4 +702,6 @@ int phsh_b200_wil_file(const char* mufftin, const char* phasout, const char* dat
     PHSH_GUARDED(phsh_b200_wil_file_impl(mufftin, phasout, dataph, zph, opts))
 }
 
+#include "phsh_cavpot_files.inc"
+
 }  // extern "C"

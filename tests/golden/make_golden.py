@@ -2,7 +2,8 @@
 """Regenerates the golden vectors under tests/golden/ -- run in the build container only (needs /root/reference).
 
 1. Re0001/*: copies of the reference's own fixture files tests/Re0001/{mufftin_Re_slab.d, dataph_Re.d,
-   leedph_Re.d, cluster_Re_*.i} (data, not source).
+   leedph_Re.d, cluster_Re_*.i, atomic_Re.i, mufftin_Re_bulk.d} (data, not source).  cluster_Re_bulk.i + atomic_Re.i ->
+   mufftin_Re_bulk.d is the reference's input/output pair of the muffin-tin potential step (CAVPOT).
 2. conphas/*: outputs of the reference's *own* Python ``phaseshifts.conphas.Conphas`` (imported from
    /root/reference with a stub ``libphsh``) run on
      - Re_A.ph   : the first section of the phasout the oracle (FP32-as-written) writes for the Re fixture,
@@ -37,7 +38,8 @@ def main():
 
     re_dir = os.path.join(HERE, "Re0001")
     os.makedirs(re_dir, exist_ok=True)
-    for f in ("mufftin_Re_slab.d", "dataph_Re.d", "leedph_Re.d", "cluster_Re_slab.i", "cluster_Re_bulk.i", "at_Re.i"):
+    for f in ("mufftin_Re_slab.d", "dataph_Re.d", "leedph_Re.d", "cluster_Re_slab.i", "cluster_Re_bulk.i", "at_Re.i",
+              "atomic_Re.i", "mufftin_Re_bulk.d"):
         shutil.copyfile(os.path.join(REF, "tests", "Re0001", f), os.path.join(re_dir, f))
 
     from oracle import fortran_io as fio
