@@ -156,7 +156,7 @@ def write_mufftin(path: str, cl, res):
     if nform == 0:
         out.append("%4d" % nr)
     if nform == 1:
-        out.append(" &NL2 NRR=%2d &END" % nr)
+        out.append(" &NL2 NRR=%2d &end" % nr)
     for ir in range(nr):
         n = int(res["npts"][ir])
         if nform == 0:
@@ -166,7 +166,7 @@ def write_mufftin(path: str, cl, res):
             for k in range(n):
                 out.append(efmt(res["r"][ir, k], 14, 5) + efmt(res["v"][ir, k], 14, 5))
         elif nform == 1:
-            out.append(" &NL16 Z=" + ffmt(cl["z"][ir], 7, 4) + ",RT=" + ffmt(cl["rmt"][ir], 7, 4) + " &END")
+            out.append(" &NL16 Z=" + ffmt(cl["z"][ir], 7, 4) + ",RT=" + ffmt(cl["rmt"][ir], 7, 4) + " &end")
             for k in range(n):
                 out.append(efmt(res["r"][ir, k], 14, 5) + efmt(res["v"][ir, k], 14, 5))
             out.append(efmt(-1.0, 14, 5))

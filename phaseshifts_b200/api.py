@@ -385,10 +385,9 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
     return out
 
 
-def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file, *, real32=True,
-                device=0):
+def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file, *, device=0):
     """``libphsh.cavpot`` with its seven arguments (``libphsh.f:2070-2071``); returns the muffin-tin zero of a bulk run."""
-    opts = _lib.FileOpts(REAL32 if real32 else 0, 0, 0, int(device))
+    opts = _lib.FileOpts(0, 0, 0, int(device))
     mtz = C.c_double(0.0)
     enc = lambda s: str(s).encode()
     _lib.check(_lib.load().phsh_b200_cavpot_file(enc(mtz_string), int(slab_flag), enc(atomic_file), enc(cluster_file),

@@ -1,4 +1,4 @@
-"""Stand-in for the f2py extension ``phaseshifts.lib.libphsh`` -- hot-path functions only.
+"""Stand-in for the f2py extension ``phaseshifts.lib.libphsh`` -- the phase-shift hot path and its producer.
 
 The reference binds three module-level callables at import (``phaseshifts/phsh.py:101-113``) and calls them
 with four *file names* (``phsh.py:326, 331, 338``; duplicate call site ``wrappers.py:632-699``):
@@ -8,9 +8,15 @@ with four *file names* (``phsh.py:326, 331, 338``; duplicate call site ``wrapper
     phsh_rel(mufftin, phasout, dataph, inpdat)   libphsh.f:4552
 
 Same names, same argument meaning, return value ``None`` like the Fortran subroutines; the contract is the
-files.  All arithmetic runs on the B200 through ``libphsh_b200.so``; there is no CPU fallback.  The
-upstream steps (``hartfock``, ``cavpot``) are NOT part of this path: if the real extension is importable
-they are delegated to it, otherwise they raise.
+files.  All arithmetic runs on the B200 through ``libphsh_b200.so``; there is no CPU fallback.
+
+The producer of the path's input is here too:
+
+    cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file) -> float
+                                                 libphsh.f:2070  (called from model.py:935)
+
+The atomic step (``hartfock``, ``hb``) is NOT part of this package: if the real extension is importable it is
+delegated to it, otherwise it raises.
 
 Environment switches (read at call time):
   PHSH_B200_DEVICE=<n>        CUDA device index (default 0)
@@ -19,6 +25,7 @@ Environment switches (read at call time):
   PHSH_B200_FAST=1            FMA-contracted integrator (not bit-faithful)
   PHSH_B200_MAX_ENERGIES=<n>  energy cap of PHSH_REL (reference: 250, libphsh.f:4642); 0 lifts it
   PHSH_B200_MAX_JRI=<n>       radial-point cap (reference: 340, libphsh.f:4609); 0 lifts it
+  PHSH_B200_CAVPOT_DELEGATE=1 hand ``cavpot`` to the real f2py extension (when importable) instead of the GPU
   PHSH_B200_CAV_ORIGINAL_HEADER=1  keep PHSH_CAV's own phasout header (NL instead of lmax), which the
                               reference's Conphas cannot parse
 """
@@ -77,12 +84,21 @@ def _upstream(name):
         if _delegate is not None and hasattr(_delegate, name):
             return getattr(_delegate, name)(*args, **kwargs)
         raise NotImplementedError(
-            "libphsh.%s is upstream of the phase-shift hot path and is not provided by phaseshifts_b200; "
-            "build the reference's Fortran extension (or supply an existing mufftin.d) for this step" % name)
+            "libphsh.%s (the atomic charge-density step) is not provided by phaseshifts_b200; build the reference's "
+            "Fortran extension or supply existing at_<element>.i files for this step" % name)
     call.__name__ = name
     return call
 
 
-cavpot = _upstream("cavpot")      # libphsh.f:2070  muffin-tin potential (step 1)
+def cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file):
+    """Muffin-tin potential of a cluster (``libphsh.f:2070-2557``): reads ``cluster.i`` + ``atomic.i``, writes
+    ``mufftin.d`` in the cluster file's NFORM, the muffin-tin zero to ``output_file`` (bulk runs) and a summary to
+    ``info_file``; returns the muffin-tin zero like the Fortran function."""
+    if _flag("PHSH_B200_CAVPOT_DELEGATE") and _delegate is not None and hasattr(_delegate, "cavpot"):
+        return _delegate.cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file)
+    return api.cavpot_file(_s(mtz_string), int(slab_flag), _s(atomic_file), _s(cluster_file), _s(mufftin_file),
+                           _s(output_file), _s(info_file), device=_int("PHSH_B200_DEVICE", 0))
+
+
 hartfock = _upstream("hartfock")  # libphsh.f:60    atomic charge densities (step 0)
 hb = _upstream("hb")              # libphsh.f:1443  helper of hartfock

@@ -1,0 +1,243 @@
+"""The muffin-tin potential step (CAVPOT) on the GPU, through the C ABI, against the CPU restatement in promoted-double
+arithmetic (oracle/cavpot_oracle.hpp) and the reference's golden pair cluster_Re_bulk.i + atomic_Re.i -> mufftin_Re_bulk.d.
+
+Tolerance: the kernel performs the oracle's operations in the oracle's order without FMA contraction; the only
+differences are CUDA's vs glibc's log / pow (<= 2 ulp), so potentials must agree to 1e-11 relative (observed 2e-16) and every
+integer quantity (mesh indices, neighbour shells, interstitial sample counts) exactly."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+RE = os.path.join(HERE, "golden", "Re0001")
+
+
+@pytest.fixture(scope="module")
+def re_case():
+    from oracle import cavpot_io as cio
+    cl = cio.read_cluster(os.path.join(RE, "cluster_Re_bulk.i"), real32=False)
+    blocks = cio.read_atomic(os.path.join(RE, "atomic_Re.i"), cl["nr"], real32=False)
+    rho = np.zeros((cl["nr"], 250))
+    nx = np.zeros(cl["nr"], dtype=np.int32)
+    for i, b in enumerate(blocks):
+        rho[i], nx[i] = cio.rela_density(b, real32=False)
+    return cl, blocks, rho, nx
+
+
+def _struct(c, **kw):
+    d = dict(spa=c["spa"], rc=c["rc"], nrr=c["nrr"], z=c["z"], zc=c["zc"], rmt=c["rmt"], rk=c["rk"],
+             dens=kw.pop("dens", np.arange(c["nr"])), alpha=c["alpha"], nh=c["nh"], nform=c["nform"])
+    d.update(kw)
+    return d
+
+
+def _check(out, t0, ref, nr):
+    """one structure of a GPU batch (first type row t0) against the oracle's result"""
+    n = ref["npts"]
+    assert list(out["npts"][t0:t0 + nr]) == list(n)
+    for i in range(nr):
+        a, b = out["pot"][t0 + i, :n[i]], ref["v"][i, :n[i]]
+        assert np.isfinite(a).all()
+        assert (np.abs(a - b) <= 1e-11 * np.maximum(1.0, np.abs(b))).all()
+
+
+def test_rela_density_interpolation_on_the_gpu(re_case):
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    cl, blocks, rho, nx = re_case
+    for i, b in enumerate(blocks):
+        g_rho, g_nx = api.cavpot_rela_density(b["rmin"], b["rmax"], b["rs"], b["iprint"])
+        assert g_nx == nx[i] == 250
+        assert np.array_equal(g_rho, rho[i])      # CHGRID is add/mul/div only: bit-identical
+    # a density whose mesh ends inside Loucks' mesh: NX is reset by CHGRID; the listing branch truncates at 1e-9
+    b = dict(blocks[0])
+    b["rmax"] = 20.0
+    for iprint in (0, 1):
+        b["iprint"] = iprint
+        o_rho, o_nx = cio.rela_density(b, real32=False)
+        g_rho, g_nx = api.cavpot_rela_density(b["rmin"], b["rmax"], b["rs"], iprint)
+        assert g_nx == o_nx and np.array_equal(g_rho[:o_nx], o_rho[:o_nx])
+    assert o_nx < 250
+
+
+@pytest.mark.parametrize("nform", [2, 0, 1])
+def test_re_bulk_matches_oracle(re_case, nform):
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    cl, _, rho, nx = re_case
+    c = dict(cl)
+    c["nform"] = nform
+    ref = cio.cavpot(c, rho, nx, real32=False)
+    out = api.cavpot_batch([_struct(c)], rho, nx, diagnostics=True)
+    _check(out, 0, ref, 2)
+    assert out["vhar"][0] == ref["vhar"] and out["vex"][0] == ref["vex"]
+    assert list(out["stats"][0][:3]) == [ref["nint"], ref["npoint"], ref["jrws"]] == [283, 1000, 199]
+    assert list(out["ncon"]) == list(ref["ncon"]) == [30, 30]
+    assert np.array_equal(out["shell_ad"], ref["ad"]) and np.array_equal(out["shell_na"], ref["na"])
+    assert np.array_equal(out["shell_ia"], ref["ia"])
+    j = ref["jrmt"][0]
+    assert np.abs(out["vh"][:, :j] - ref["vh"][:, :j]).max() <= 1e-11 * np.abs(ref["vh"][:, :j]).max()
+    assert np.abs(out["vs"][:, :j] - ref["vs"][:, :j]).max() <= 1e-11 * np.abs(ref["vs"][:, :j]).max()
+
+
+def test_slab_mtzm_and_madelung_branches(re_case):
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    cl, _, rho, nx = re_case
+    slab = cio.read_cluster(os.path.join(RE, "cluster_Re_slab.i"), real32=False)
+    ref = cio.cavpot(slab, rho, nx, slab=1, esht=-1.6425, real32=False)
+    out = api.cavpot_batch([_struct(slab, slab=1, esht=-1.6425)], rho, nx, diagnostics=True)
+    _check(out, 0, ref, 2)
+    assert out["stats"][0][0] == ref["nint"] == 933
+    # MTZM: NH = 0 with one atom type (spherical average between R_mt and R_ws)
+    c1 = dict(cl)
+    c1.update(nh=0, nr=1, nrr=np.array([2], dtype=np.int32), z=cl["z"][:1], zc=cl["zc"][:1], rmt=cl["rmt"][:1])
+    ref = cio.cavpot(c1, rho[:1], nx[:1], real32=False)
+    out = api.cavpot_batch([_struct(c1, dens=[0])], rho[:1], nx[:1])
+    _check(out, 0, ref, 1)
+    assert abs(out["mtz"][0] - ref["mtz"]) <= 1e-12
+    # MAD: a non-zero valence switches the Ewald sums on (exp/sin/cos on the device: looser)
+    c2 = dict(cl)
+    c2["zc"] = np.array([1.0, -1.0])
+    ref = cio.cavpot(c2, rho, nx, real32=False)
+    out = api.cavpot_batch([_struct(c2)], rho, nx, diagnostics=True)
+    j = ref["jrmt"][0]
+    assert np.abs(ref["vmad"][:, :j]).max() > 0.05
+    assert np.abs(out["vmad"][:, :j] - ref["vmad"][:, :j]).max() <= 1e-10
+    n = ref["npts"][0]
+    assert np.abs(out["pot"][:, :n] - ref["v"][:, :n]).max() <= 1e-9
+    # NH = 0 with two atom types: no muffin-tin zero is computed at all (VHAR = VEX = 0)
+    c3 = dict(cl)
+    c3["nh"] = 0
+    ref = cio.cavpot(c3, rho, nx, real32=False)
+    out = api.cavpot_batch([_struct(c3)], rho, nx)
+    assert out["mtz"][0] == 0.0 == ref["mtz"]
+    _check(out, 0, ref, 2)
+
+
+def test_ragged_batch_of_perturbed_structures(re_case):
+    """64 structures of 1-3 atom types / 1-4 atoms with jittered radii, positions, exchange parameters, sampling grids
+    (NH=1 lands inside a sphere first and is doubled) and three different charge densities, in one launch."""
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    cl, _, rho0, nx0 = re_case
+    rng = np.random.default_rng(77)
+    rho = np.stack([rho0[0], 0.6 * rho0[0], 0.3 * rho0[0]])
+    zel = np.array([75.0, 45.0, 22.0])
+    nx = np.array([250, 240, 231], dtype=np.int32)
+    structs, cls = [], []
+    for s in range(64):
+        nr = int(rng.integers(1, 4))
+        nrr = rng.integers(1, 3, size=nr).astype(np.int32) if nr < 3 else np.ones(nr, dtype=np.int32)
+        n = int(nrr.sum())
+        base = np.array([[0.0, 0.0, 0.0], [-0.5, 0.2887, -0.8072], [0.5, 0.2887, 0.8], [0.0, 0.5774, 0.1]])[:n]
+        dens = rng.integers(0, 3, size=nr)
+        c = dict(spa=cl["spa"] * (1 + 0.05 * rng.uniform(-1, 1)), rc=cl["rc"] * np.array([[1, 1, 1], [1, 1, 1], [1, 1, 1.5 if n > 2 else 1]]),
+                 nr=nr, nrr=nrr, z=zel[dens], zc=np.zeros(nr), rmt=2.2 + 0.3 * rng.uniform(-1, 1, size=nr),
+                 rk=base + 0.02 * rng.normal(size=base.shape), nform=int(rng.integers(0, 3)), alpha=0.7 + 0.05 * rng.uniform(),
+                 nh=int(rng.choice([1, 2, 5, 8])))
+        cls.append((c, dens))
+        structs.append(_struct(c, dens=dens))
+    out = api.cavpot_batch(structs, rho, nx, diagnostics=True)
+    assert out["type_off"][-1] == sum(c["nr"] for c, _ in cls)
+    for s, (c, dens) in enumerate(cls):
+        ref = cio.cavpot(c, rho[dens], nx[dens], real32=False)
+        t0 = out["type_off"][s]
+        _check(out, t0, ref, c["nr"])
+        assert list(out["stats"][s][:2]) == [ref["nint"], ref["npoint"]]
+        assert abs(out["mtz"][s] - ref["mtz"]) <= 1e-12 * max(1.0, abs(ref["mtz"]))
+        assert np.array_equal(out["shell_na"][t0:t0 + c["nr"]], ref["na"])
+
+
+def _values(path):
+    lines = open(path).read().split("\n")
+    blocks, i = [], 0
+    while i + 2 < len(lines) and lines[i].strip():
+        n = int(lines[i + 2][14:18])
+        rows = -(-n // 5)
+        vals = []
+        for ln in lines[i + 3:i + 3 + rows]:
+            vals += [float(ln[k:k + 14]) for k in range(0, len(ln.rstrip()), 14)]
+        blocks.append((lines[i].rstrip(), lines[i + 1], lines[i + 2], np.array(vals)))
+        i += 3 + rows
+    return blocks
+
+
+def test_file_interface_against_golden_and_oracle_files(tmp_path):
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import libphsh
+    g = [str(tmp_path / n) for n in ("g_mufftin.d", "g_bmtz.i", "g_info.txt")]
+    o = [str(tmp_path / n) for n in ("o_mufftin.d", "o_bmtz.i", "o_info.txt")]
+    mtz = libphsh.cavpot("", 0, os.path.join(RE, "atomic_Re.i"), os.path.join(RE, "cluster_Re_bulk.i"), *g)
+    omtz, _, _ = cio.cavpot_file("", 0, os.path.join(RE, "atomic_Re.i"), os.path.join(RE, "cluster_Re_bulk.i"), *o, real32=False)
+    assert isinstance(mtz, float) and abs(mtz - omtz) < 1e-6 and abs(float(open(g[1]).read()) - mtz) < 1e-6
+    la, lb = open(g[0]).read().split("\n"), open(o[0]).read().split("\n")
+    assert len(la) == len(lb) == 137
+    differing = [i for i, (x, y) in enumerate(zip(la, lb)) if x != y]
+    assert len(differing) <= 2       # a last-digit flip where a value sits on a rounding boundary, at most
+    gold = _values(os.path.join(RE, "mufftin_Re_bulk.d"))
+    mine = _values(g[0])
+    for (gn, gh, gz, gv), (mn, mh, mz, mv) in zip(gold, mine):
+        assert gn == mn and gz == mz and gh[:47] == mh[:47]
+        assert np.abs(gv - mv).max() < 6e-4   # the fixture's own REAL*4 noise (see tests/test_cavpot_oracle.py)
+    assert "MUFFIN-TIN ZERO" in open(g[2]).read()
+    # slab run: potential shifted by (esht - MTZ); the MTZ file stays empty like the Fortran leaves it
+    s = [str(tmp_path / n) for n in ("s_mufftin.d", "s_mtz.i", "s_info.txt")]
+    r = libphsh.cavpot("%.6f" % (mtz + 0.5), 1, os.path.join(RE, "atomic_Re.i"), os.path.join(RE, "cluster_Re_bulk.i"), *s)
+    assert abs(r - (mtz + 0.5)) < 1e-6 and os.path.getsize(s[1]) == 0
+    sv = _values(s[0])
+    rgrid = 60.0 * np.exp(0.03125 * (np.arange(1, 322) - 421))
+    assert np.allclose(sv[0][3] - mine[0][3], -0.5 * rgrid, atol=1.1e-4)   # 7 printed digits of values up to 150
+
+
+def test_chain_cluster_to_phase_shifts_matches_golden_leedph(tmp_path, monkeypatch):
+    """cluster.i + atomic.i -> cavpot -> phsh_rel -> conphas entirely on this package's code: the .phs table agrees with
+    the reference's golden leedph_Re.d to two units of its 4th decimal (its potentials were made in REAL*4)."""
+    from phaseshifts_b200 import api, libphsh
+    from phaseshifts_b200.conphas import Conphas
+    muff = str(tmp_path / "mufftin.d")
+    libphsh.cavpot("", 0, os.path.join(RE, "atomic_Re.i"), os.path.join(RE, "cluster_Re_bulk.i"), muff, str(tmp_path / "bmtz.i"),
+                   str(tmp_path / "info.txt"))
+    libphsh.phsh_rel(muff, str(tmp_path / "phasout"), str(tmp_path / "dataph"), str(tmp_path / "inpdat"))
+    monkeypatch.chdir(tmp_path)
+    files = Conphas.split_phasout(str(tmp_path / "phasout"), output_filenames=[str(tmp_path / "A.ph"), str(tmp_path / "B.ph")])
+    con = Conphas(input_files=[files[0]], output_file=str(tmp_path / "A.phs"), formatting="cleed", lmax=10)
+    con.calculate()
+    lines = open(tmp_path / "A.phs").read().splitlines()
+    gl = open(os.path.join(RE, "leedph_Re.d")).read().splitlines()
+    got = np.array([[float(x) for x in lines[2 + 2 * i].replace("-", " -").split()] for i in range(57)])
+    gold = np.array([[float(x) for x in gl[2 * i + 1].replace("-", " -").split()] for i in range(57)])
+    assert np.abs(got - gold).max() <= 2.5e-4
+
+
+def test_error_behaviour(tmp_path):
+    from phaseshifts_b200 import api, PhshB200Error
+    ok_c, ok_a = os.path.join(RE, "cluster_Re_bulk.i"), os.path.join(RE, "atomic_Re.i")
+    outs = [str(tmp_path / n) for n in ("m.d", "b.i", "i.txt")]
+    with pytest.raises(PhshB200Error) as e:
+        api.cavpot_file("", 0, ok_a, str(tmp_path / "nope.i"), *outs)
+    assert e.value.code == -4
+    trunc = tmp_path / "trunc.i"
+    trunc.write_text("".join(open(ok_c).readlines()[:8]))
+    with pytest.raises(PhshB200Error) as e:
+        api.cavpot_file("", 0, ok_a, str(trunc), *outs)
+    assert e.value.code == -1
+    herm = tmp_path / "herm.i"
+    herm.write_text("HERM\n" + "".join(open(ok_a).readlines()[1:]))
+    with pytest.raises(PhshB200Error) as e:
+        api.cavpot_file("", 0, str(herm), ok_c, *outs)
+    assert e.value.code == -1 and "RELA" in str(e.value)
+    with pytest.raises(PhshB200Error):
+        api.cavpot_file("not-a-number", 1, ok_a, ok_c, *outs)
+    # a muffin-tin radius off Loucks' mesh, or overlapping spheres that leave no interstitial point, are refused / reported
+    from oracle import cavpot_io as cio
+    cl = cio.read_cluster(ok_c, real32=False)
+    rho = np.ones((2, 250))
+    nx = np.array([250, 250], dtype=np.int32)
+    bad = _struct(cl)
+    bad["rmt"] = np.array([2.6, 50.0])
+    with pytest.raises(PhshB200Error):
+        api.cavpot_batch([bad], rho, nx)
+    assert api.cavpot_batch([], rho, nx)["pot"].shape == (0, 421)

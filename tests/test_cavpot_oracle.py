@@ -1,0 +1,124 @@
+"""The CAVPOT oracle (oracle/cavpot_oracle.hpp) pinned on the reference's own input/output pair of the muffin-tin
+potential step: tests/Re0001/{cluster_Re_bulk.i, atomic_Re.i} -> mufftin_Re_bulk.d (committed under tests/golden/Re0001).
+CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cavpot_io as cio
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RE = os.path.join(HERE, "golden", "Re0001")
+
+
+def _values(path):
+    """The tabulated r*V values of an NFORM=2 mufftin.d, block by block."""
+    lines = open(path).read().split("\n")
+    blocks, i = [], 0
+    while i + 2 < len(lines) and lines[i].strip():
+        n = int(lines[i + 2][14:18])
+        rows = -(-n // 5)
+        vals = []
+        for ln in lines[i + 3:i + 3 + rows]:
+            vals += [float(ln[k:k + 14]) for k in range(0, len(ln.rstrip()), 14)]
+        blocks.append((lines[i].rstrip(), lines[i + 1], lines[i + 2], np.array(vals)))
+        i += 3 + rows
+    return blocks
+
+
+@pytest.fixture(scope="module")
+def runs(tmp_path_factory):
+    out = {}
+    d = tmp_path_factory.mktemp("cavpot")
+    for real32 in (True, False):
+        muff = str(d / ("mufftin_%d.d" % real32))
+        mtz, res, cl = cio.cavpot_file("", 0, os.path.join(RE, "atomic_Re.i"), os.path.join(RE, "cluster_Re_bulk.i"), muff,
+                                       str(d / ("bmtz_%d.txt" % real32)), str(d / ("info_%d.txt" % real32)), real32=real32)
+        out[real32] = (mtz, res, cl, muff, str(d / ("bmtz_%d.txt" % real32)))
+    return out
+
+
+def test_as_written_arithmetic_reproduces_the_reference_mufftin(runs):
+    """REAL*4 as written: 97 % of the 642 tabulated values within one unit of the 7th printed digit of the reference's
+    file, all within four units (a few REAL*4 ulps; the fixture was made with another libm) -- or 2e-5 absolute where r*(V - VINT) has cancelled to below 10 (VINT itself carries the REAL*4
+    rounding of a 283-term sum evaluated with another libm) -- and more than three quarters of them digit for digit."""
+    gold = _values(os.path.join(RE, "mufftin_Re_bulk.d"))
+    mine = _values(runs[True][3])
+    assert len(gold) == len(mine) == 2
+    exact = total = 0
+    for (gn, gh, gz, gv), (mn, mh, mz, mv) in zip(gold, mine):
+        assert gn == mn and gz == mz          # name; Z, RMT, number of points (321)
+        assert gh[:47] == mh[:47]             # ES, DE, UE, LSM (the fixture's VINT column reads 0: see DESIGN.md)
+        assert gv.shape == mv.shape == (321,)
+        unit = 10.0 ** (np.floor(np.log10(np.abs(gv))) + 1 - 7)
+        assert (np.abs(gv - mv) <= np.maximum(4.0001 * unit, 2e-5)).all()
+        assert (np.abs(gv - mv) <= np.maximum(1.0001 * unit, 2e-5)).mean() > 0.97
+        exact += int((gv == mv).sum())
+        total += gv.size
+    assert total == 642 and exact / total > 0.75
+
+
+def test_promoted_arithmetic_stays_within_the_real4_noise_of_the_fixture(runs):
+    gold = _values(os.path.join(RE, "mufftin_Re_bulk.d"))
+    mine = _values(runs[False][3])
+    for (_, _, _, gv), (_, _, _, mv) in zip(gold, mine):
+        assert np.abs(gv - mv).max() < 6e-4   # REAL*4 cancellation in the reference's own sums (MTZ: 3.6e-4 Ryd)
+    assert abs(runs[False][0] - runs[True][0]) < 5e-4
+
+
+def test_structure_quantities(runs):
+    mtz, res, cl, _, bm = runs[True]
+    assert res["nint"] == 283 and res["npoint"] == 1000 and res["jrws"] == 199
+    assert list(res["jrmt"]) == [197, 197] and list(res["npts"]) == [321, 321] and list(res["ncon"]) == [30, 30]
+    assert res["ad"][0][0] == 0.0 and res["ia"][0][0] == 1 and res["na"][0][0] == 1   # the atom itself
+    assert res["ia"][1][0] == 2
+    assert (np.diff(res["ad"][0]) > -1e-4).all()
+    # hcp: 6 + 6 nearest neighbours at ~a (split by the rounded input coordinates)
+    near = res["ad"][0] < 5.3
+    assert res["na"][0][near].sum() == 1 + 12
+    assert abs(mtz - (-1.6429)) < 1e-3
+    assert abs(float(open(bm).read()) - mtz) < 1e-6
+
+
+def test_slab_shift_and_other_forms(tmp_path):
+    cl = cio.read_cluster(os.path.join(RE, "cluster_Re_bulk.i"), real32=False)
+    blocks = cio.read_atomic(os.path.join(RE, "atomic_Re.i"), cl["nr"], real32=False)
+    rho = np.zeros((2, 250))
+    nx = np.zeros(2, dtype=np.int32)
+    for i, b in enumerate(blocks):
+        rho[i], nx[i] = cio.rela_density(b, real32=False)
+    assert list(nx) == [250, 250] and (rho[:, :200] > 0).all()
+    base = cio.cavpot(cl, rho, nx, real32=False)
+    # a slab run with esht = own MTZ changes nothing; esht = MTZ + d shifts V by -d, i.e. r*V by -d*r
+    same = cio.cavpot(cl, rho, nx, slab=1, esht=base["mtz"], real32=False)
+    assert np.abs(same["v"] - base["v"]).max() < 1e-12
+    sh = cio.cavpot(cl, rho, nx, slab=1, esht=base["mtz"] + 0.25, real32=False)
+    n = base["npts"][0]
+    assert np.allclose(sh["v"][0, :n] - base["v"][0, :n], -0.25 * base["r"][0, :n], atol=2e-6)
+    # NFORM 0 tabulates V, NFORM 1 r*V, on Loucks' mesh out to JRMT
+    c0, c1 = dict(cl), dict(cl)
+    c0["nform"], c1["nform"] = 0, 1
+    r0, r1 = cio.cavpot(c0, rho, nx, real32=False), cio.cavpot(c1, rho, nx, real32=False)
+    assert list(r0["npts"]) == [197, 197]
+    assert np.allclose(r1["v"][0, :197], r0["v"][0, :197] * r0["r"][0, :197], rtol=1e-14)
+    assert np.allclose(r0["r"][0, :3], np.exp(-8.8 + 0.05 * np.arange(3)), rtol=1e-6)
+    for c, name in ((c0, "m0.d"), (c1, "m1.d")):
+        cio.write_mufftin(str(tmp_path / name), c, cio.cavpot(c, rho, nx, real32=False))
+    assert open(tmp_path / "m0.d").readline() == "   2\n"
+    assert open(tmp_path / "m1.d").readline() == " &NL2 NRR= 2 &end\n"
+
+
+def test_asbuilt_nbr_leaves_the_type_loop_early():
+    """libphsh.f:3293-3398: `exit` instead of `GOTO 9` -- the second atom type loses most of its neighbour shells."""
+    cl = cio.read_cluster(os.path.join(RE, "cluster_Re_bulk.i"), real32=True)
+    blocks = cio.read_atomic(os.path.join(RE, "atomic_Re.i"), cl["nr"], real32=True)
+    rho = np.zeros((2, 250))
+    nx = np.zeros(2, dtype=np.int32)
+    for i, b in enumerate(blocks):
+        rho[i], nx[i] = cio.rela_density(b, real32=True)
+    good = cio.cavpot(cl, rho, nx, real32=True)
+    bad = cio.cavpot(cl, rho, nx, real32=True, asbuilt=True)
+    assert list(good["ncon"]) == [30, 30]
+    assert bad["na"][1].sum() < good["na"][1].sum()
+    assert np.abs(bad["v"][1, :321] - good["v"][1, :321]).max() > 1e-3
