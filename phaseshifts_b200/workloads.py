@@ -167,3 +167,46 @@ def c5_wil(P=65536, ne=500, nl=13, nr=101, seed=5, first=0):
         Z[b0:b0 + n], RT[b0:b0 + n] = z, rt
     e = np.float32(1.5) + np.arange(ne).astype(np.float32) * ((np.float32(75.0) - np.float32(1.5)) / np.float32(max(ne - 1, 1)))
     return dict(rs=rs, zs=zs, nrows=nrows, Z=Z, RT=RT, e=np.asarray(e, dtype=np.float64), NL=nl, NR=nr)
+
+
+RE_CLUSTER = os.path.join(_ROOT, "tests", "golden", "Re0001", "cluster_Re_bulk.i")
+RE_ATOMIC = os.path.join(_ROOT, "tests", "golden", "Re0001", "atomic_Re.i")
+
+
+def read_rela_blocks(path, n_blocks):
+    """The 'RELA' blocks of an atomic.i (libphsh.f:3469-3481): dicts with rmin, rmax, rs, iprint."""
+    lines = open(path).read().split("\n")
+    pos, out = 0, []
+    for _ in range(n_blocks):
+        if lines[pos][:4] != "RELA":
+            raise ValueError("%s: block %d is not a RELA charge density" % (path, len(out) + 1))
+        iprint = int(lines[pos + 2][:4] or 0)
+        m = lines[pos + 3].ljust(40)
+        rmin, rmax, n = float(m[:15].replace("D", "E")), float(m[15:30].replace("D", "E")), int(m[30:35])
+        rs = np.array([float(x[:15]) for x in lines[pos + 4:pos + 4 + n]])
+        out.append(dict(rmin=rmin, rmax=rmax, rs=rs, iprint=iprint))
+        pos += 4 + n
+    return out
+
+
+def c6_cavpot(S=4096, seed=6, first=0, nh=10):
+    """C6 (producer of the C4 sweep): S perturbed Re(0001) bulk cells through the muffin-tin potential step.
+
+    Base = the reference's fixture cluster_Re_bulk.i (hcp, two atom types, NFORM=2, alpha=0.7267, NH=10) with the
+    charge density of atomic_Re.i; per structure R_mt = 2.6*(1+0.1*U(-1,1)) for both types, the second atom displaced
+    by N(0, 0.01) (units of the lattice constant) and c/a scaled by 1+0.02*U(-1,1).  Returns the structures for
+    ``api.cavpot_batch`` plus the RELA block the densities come from (interpolate with ``api.cavpot_rela_density``).
+    """
+    rc = np.array([[0.5, 0.8660, 0.0], [0.5, -0.8660, 0.0], [0.0, 0.0, 1.6045]])
+    rk = np.array([[0.0, 0.0, 0.0], [-0.5, 0.2887, -0.8072]])
+    structs = []
+    for s in range(S):
+        rng = np.random.default_rng([seed, first + s])
+        rmt = np.round(2.6 * (1.0 + 0.1 * rng.uniform(-1, 1)), 4)
+        pos = rk.copy()
+        pos[1] += np.round(0.01 * rng.normal(size=3), 4)
+        cell = rc.copy()
+        cell[2, 2] = np.round(1.6045 * (1.0 + 0.02 * rng.uniform(-1, 1)), 4)
+        structs.append(dict(spa=5.2156, rc=cell, nrr=[1, 1], z=[75.0, 75.0], zc=[0.0, 0.0], rmt=[rmt, rmt], rk=pos,
+                            dens=[0, 0], alpha=0.7267, nh=nh, nform=2))
+    return dict(structures=structs, rela=read_rela_blocks(RE_ATOMIC, 1)[0])

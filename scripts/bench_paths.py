@@ -88,6 +88,34 @@ def main():
                     units=out.numel(), gpu_ms=ms, gpu_units_per_s=out.numel() / ms * 1e3,
                     cpu_units_per_s=ref.size / cpu, cpu_threads=nt, cpu_sample="first %d potentials" % n,
                     max_abs_err=float(np.abs(out[:n].cpu().numpy() - ref).max())))
+    # C6: the producer of the sweep's potentials -- muffin-tin potential step for a batch of perturbed cells
+    from oracle import cavpot_io as cio
+    w = workloads.c6_cavpot()
+    b = w["rela"]
+    rho0, nx0 = api.cavpot_rela_density(b["rmin"], b["rmax"], b["rs"], b["iprint"])
+    rho, nxs = rho0[None, :], np.array([nx0], dtype=np.int32)
+    t0 = time.perf_counter()
+    out = api.cavpot_batch(w["structures"], rho, nxs)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        out = api.cavpot_batch(w["structures"], rho, nxs)
+    ms = (time.perf_counter() - t0) / reps * 1e3   # host API: packing, H2D, one launch, D2H
+    n = 4 * nt
+    t0 = time.perf_counter()
+    err = 0.0
+    for s in range(n):   # the oracle is single-threaded per structure; n structures, serial
+        st = w["structures"][s]
+        c = dict(spa=st["spa"], rc=st["rc"], nr=2, nrr=np.array(st["nrr"], dtype=np.int32), z=np.array(st["z"]),
+                 zc=np.array(st["zc"]), rmt=np.array(st["rmt"]), rk=st["rk"], nform=2, alpha=st["alpha"], nh=st["nh"])
+        r = cio.cavpot(c, np.stack([rho0, rho0]), np.array([nx0, nx0], dtype=np.int32), real32=False)
+        k = r["npts"][0]
+        err = max(err, float(np.abs(out["pot"][2 * s, :k] - r["v"][0, :k]).max()))
+    cpu = time.perf_counter() - t0
+    S = len(w["structures"])
+    res.append(dict(config="C6 producer: 4096 perturbed Re(0001) cells (2 atom types, NH=10) through cavpot, host API",
+                    units=S, gpu_ms=ms, gpu_units_per_s=S / ms * 1e3, cpu_units_per_s=n / cpu, cpu_threads=1,
+                    cpu_sample="first %d structures, one thread" % n, max_abs_err=err, unit="structures"))
     for r in res:
         r["speedup_vs_cpu_threads"] = r["gpu_units_per_s"] / r["cpu_units_per_s"]
         print(json.dumps(r), flush=True)

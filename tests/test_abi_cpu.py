@@ -125,10 +125,14 @@ def test_standin_module_surface(monkeypatch):
     from phaseshifts_b200 import libphsh, api
     for fn in ("phsh_rel", "phsh_cav", "phsh_wil"):
         assert len(inspect.signature(getattr(libphsh, fn)).parameters) == 4
-    for fn in ("cavpot", "hartfock", "hb"):
+    assert len(inspect.signature(libphsh.cavpot).parameters) == 7   # libphsh.f:2070-2071
+    for fn in ("hartfock", "hb"):
         with pytest.raises(NotImplementedError):
             getattr(libphsh, fn)(1, 2)
     seen = {}
+    monkeypatch.setattr(api, "cavpot_file", lambda *a, **k: seen.update(cav=a, cavkw=k) or -1.5)
+    assert libphsh.cavpot(b" -1.0 ", 1, "a.i ", "c.i", "m.d", "o.i", "info.txt") == -1.5
+    assert seen["cav"] == ("-1.0", 1, "a.i", "c.i", "m.d", "o.i", "info.txt") and seen["cavkw"] == {"device": 0}
     monkeypatch.setattr(api, "phsh_rel_file", lambda *a, **k: seen.update(args=a, kw=k))
     monkeypatch.setenv("PHSH_B200_MAX_ENERGIES", "0")
     monkeypatch.setenv("PHSH_B200_REAL32", "1")

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "phaseshifts
 
 
 @pytest.fixture()
-def wired(monkeypatch, tmp_path):
+def wired(monkeypatch, tmp_path, request):
     if REF not in sys.path:
         monkeypatch.syspath_prepend(REF)
     from phaseshifts_b200 import api, backend, libphsh, _lib
@@ -35,12 +35,20 @@ def wired(monkeypatch, tmp_path):
                               jri_cap=max_jri)
         monkeypatch.setattr(api, "phsh_rel_file", fake_rel_file)
 
+        from oracle import cavpot_io as cio
+
+        def fake_cavpot_file(mtz_string, slab, atomic_file, cluster_file, mufftin_file, output_file, info_file, device=0):
+            return cio.cavpot_file(mtz_string, slab, atomic_file, cluster_file, mufftin_file, output_file, info_file,
+                                   real32=False)[0]
+        monkeypatch.setattr(api, "cavpot_file", fake_cavpot_file)
+
     def replay_cavpot(mtz_string, slab, atomic_file, cluster_file, mufftin_file, output_file, info_file):
         shutil.copyfile(os.path.join(RE, "mufftin_Re_slab.d"), mufftin_file)
         with open(output_file, "w") as f:
             f.write("0.0\n")
         return 0.0
-    monkeypatch.setattr(libphsh, "cavpot", replay_cavpot)
+    if not getattr(request, "param", False):
+        monkeypatch.setattr(libphsh, "cavpot", replay_cavpot)
     work = tmp_path / "work"
     work.mkdir()
     shutil.copyfile(os.path.join(RE, "at_Re.i"), work / "at_Re.i")  # skips the hartfock step (phsh.py:195-200)
@@ -80,6 +88,31 @@ def test_unchanged_wrapper_through_b200_backend_matches_golden_leedph(wired):
         got = np.array([[float(x) for x in lines[2 + 2 * i].replace("-", " -").split()] for i in range(57)])
         assert np.abs(got - gold).max() <= 1.0001e-4
     assert os.path.exists(work / "cluster_Re_slab_phasout.i") and os.path.exists(work / "cluster_Re_slab_inpdat.txt")
+
+
+@pytest.mark.parametrize("wired", [True], indirect=True)
+def test_unchanged_wrapper_with_our_cavpot_step(wired):
+    """Nothing replayed: the unmodified Wrapper writes cluster/atomic inputs, `libphsh.cavpot` (this package) turns them
+    into mufftin.d for the bulk and the slab run, `libphsh.phsh_rel` into phasout, the reference's Conphas into .phs.
+    The bulk cluster reproduces the golden leedph to two units of its 4th decimal (REAL*4 noise of the fixture's
+    potentials); the slab cluster (20-bohr vacuum cell) is a different potential and only has to be well formed."""
+    import phaseshifts.backends as B
+    _, work = wired
+    files = B.get_backend("b200").autogen_from_input(os.path.join(RE, "cluster_Re_bulk.i"),
+                                                     os.path.join(RE, "cluster_Re_bulk.i"), tmp_dir=str(work),
+                                                     lmax=10, format="cleed")
+    assert len(files) == 2
+    gold = _leedph()
+    for f in files:
+        lines = open(f).read().splitlines()
+        got = np.array([[float(x) for x in lines[2 + 2 * i].replace("-", " -").split()] for i in range(57)])
+        assert np.abs(got - gold).max() <= 2.5e-4
+    muff = [f for f in os.listdir(work) if f.endswith("mufftin.d")]
+    assert muff and open(work / muff[0]).read().splitlines()[2].split() == ["75", "2.600000", "321"]
+    files = B.get_backend("b200").autogen_from_input(os.path.join(RE, "cluster_Re_bulk.i"),
+                                                     os.path.join(RE, "cluster_Re_slab.i"), tmp_dir=str(work),
+                                                     lmax=10, format="cleed")
+    assert len(files) == 2 and all(open(f).readline().startswith("57 10 neng lmax") for f in files)
 
 
 def test_cli_route_with_energy_range(wired, monkeypatch, capsys):
