@@ -317,18 +317,9 @@ def cavpot_rela_density(rmin, rmax, rs, iprint=0, device=0):
     return rho, int(nx.value)
 
 
-def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
-    """The muffin-tin potential step of ``libphsh.cavpot`` (``libphsh.f:2070-2557``) for a batch of structures.
-
-    ``structures``: sequence of dicts with ``spa`` (lattice constant, bohr), ``rc`` [3][3] (axis j = ``rc[j]``, in units of
-    ``spa``), ``nrr`` [nr], ``z`` [nr], ``zc`` [nr], ``rmt`` [nr], ``rk`` [n_atoms][3] (units of ``spa``, listed type by type),
-    ``dens`` [nr] (row of ``rho`` for each atom type), ``alpha``, ``nh``, ``nform`` and optionally ``slab`` / ``esht``.
-    ``rho`` [n_dens][250], ``nx`` [n_dens]: the atomic charge densities on Loucks' mesh (``cavpot_rela_density``).
-
-    Returns a dict: ``mtz`` [S] (VHAR+VEX, what ``cavpot`` returns for a bulk run), ``vhar``, ``vex`` [S], ``npts`` [T],
-    ``pot`` [T][421], ``type_off`` [S+1]; with ``diagnostics`` also ``vh``, ``vs``, ``vmad`` [T][250], the neighbour shells
-    ``shell_ad/na/ia`` [T][30], ``ncon`` [T] and ``stats`` [S][4] (NINT, NPOINT, JRWS, NH after doubling).
-    """
+def cavpot_pack(structures):
+    """Flatten a sequence of structure dicts (see ``cavpot_batch``) into the ragged arrays of ``phsh_b200_cavpot_batch``.
+    Lengths are multiplied by the lattice constant here, as ``CAVPOT`` does on input (``libphsh.f:2133-2137, 2209-2211``)."""
     S = len(structures)
     type_off = np.zeros(S + 1, dtype=np.int32)
     atom_off = np.zeros(S + 1, dtype=np.int32)
@@ -344,8 +335,8 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
         pos = np.asarray(st["rk"], dtype=np.float64).reshape(-1, 3)
         type_off[s + 1] = type_off[s] + n_r.size
         atom_off[s + 1] = atom_off[s] + pos.shape[0]
-        rc.append(spa * np.asarray(st["rc"], dtype=np.float64).reshape(9))  # RC(I,J)=SPA*RC(I,J) (libphsh.f:2133-2137)
-        rk.append(spa * pos)
+        rc.append(spa * np.asarray(st["rc"], dtype=np.float64).reshape(9))
+        rk.append((spa * pos).reshape(-1))
         nrr.append(n_r)
         z.append(np.asarray(st["z"], dtype=np.float64).reshape(-1))
         zc.append(np.asarray(st["zc"], dtype=np.float64).reshape(-1))
@@ -353,34 +344,60 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
         dens.append(np.asarray(st["dens"], dtype=np.int32).reshape(-1))
         alpha[s], nh[s], nform[s] = float(st["alpha"]), int(st["nh"]), int(st["nform"])
         slab[s], esht[s] = int(st.get("slab", 0)), float(st.get("esht", 0.0))
-    T, A = int(type_off[-1]), int(atom_off[-1])
     cat = lambda parts, dt: np.ascontiguousarray(np.concatenate(parts) if parts else np.zeros(0), dtype=dt)
-    rc, rk = cat(rc, np.float64), cat([r.reshape(-1) for r in rk], np.float64)
-    nrr, z, zc, rmt, dens = cat(nrr, np.int32), cat(z, np.float64), cat(zc, np.float64), cat(rmt, np.float64), cat(dens, np.int32)
+    return dict(type_off=type_off, atom_off=atom_off, rc=cat(rc, np.float64), nrr=cat(nrr, np.int32), z=cat(z, np.float64),
+                zc=cat(zc, np.float64), rmt=cat(rmt, np.float64), dens=cat(dens, np.int32), rk=cat(rk, np.float64), alpha=alpha,
+                nh=nh, slab=slab, esht=esht, nform=nform)
+
+
+_CAVPOT_FIELDS = (("type_off", np.int32), ("atom_off", np.int32), ("rc", np.float64), ("nrr", np.int32), ("z", np.float64),
+                  ("zc", np.float64), ("rmt", np.float64), ("dens", np.int32), ("rk", np.float64), ("alpha", np.float64),
+                  ("nh", np.int32), ("slab", np.int32), ("esht", np.float64), ("nform", np.int32))
+
+
+def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
+    """The muffin-tin potential step of ``libphsh.cavpot`` (``libphsh.f:2070-2557``) for a batch of structures.
+
+    ``structures``: sequence of dicts with ``spa`` (lattice constant, bohr), ``rc`` [3][3] (axis j = ``rc[j]``, in units of
+    ``spa``), ``nrr`` [nr], ``z`` [nr], ``zc`` [nr], ``rmt`` [nr], ``rk`` [n_atoms][3] (units of ``spa``, listed type by type),
+    ``dens`` [nr] (row of ``rho`` for each atom type), ``alpha``, ``nh``, ``nform`` and optionally ``slab`` / ``esht`` -- or the
+    dict of flat arrays ``cavpot_pack`` makes of such a sequence (lengths in bohr), which skips the per-structure Python work.
+    ``rho`` [n_dens][250], ``nx`` [n_dens]: the atomic charge densities on Loucks' mesh (``cavpot_rela_density``).
+
+    Returns a dict: ``mtz`` [S] (VHAR+VEX, what ``cavpot`` returns for a bulk run), ``vhar``, ``vex`` [S], ``npts`` [T],
+    ``pot`` [T][421], ``type_off`` [S+1]; with ``diagnostics`` also ``vh``, ``vs``, ``vmad`` [T][250], the neighbour shells
+    ``shell_ad/na/ia`` [T][30], ``ncon`` [T] and ``stats`` [S][4] (NINT, NPOINT, JRWS, NH after doubling).
+    """
+    pk = structures if isinstance(structures, dict) else cavpot_pack(structures)
+    keep = {k: np.ascontiguousarray(pk[k], dtype=dt).reshape(-1) for k, dt in _CAVPOT_FIELDS}
+    S = keep["type_off"].size - 1
+    T, A = (int(keep["type_off"][-1]), int(keep["atom_off"][-1])) if S > 0 else (0, 0)
     rho = np.ascontiguousarray(np.asarray(rho, dtype=np.float64).reshape(-1, 250))
     nx = np.ascontiguousarray(np.asarray(nx, dtype=np.int32).reshape(-1))
-    for name, arr in (("z", z), ("zc", zc), ("rmt", rmt), ("dens", dens)):
-        if arr.size != T:
-            raise ValueError("%s has %d entries for %d atom types" % (name, arr.size, T))
+    for name, n in (("rc", 9 * S), ("rk", 3 * A), ("nrr", T), ("z", T), ("zc", T), ("rmt", T), ("dens", T), ("alpha", S),
+                    ("nh", S), ("slab", S), ("esht", S), ("nform", S)):
+        if keep[name].size != n:
+            raise ValueError("%s has %d entries, expected %d" % (name, keep[name].size, n))
+    if nx.size != rho.shape[0]:
+        raise ValueError("nx has %d entries for %d densities" % (nx.size, rho.shape[0]))
+    keep.update(rho=rho, nx=nx)
     b = _lib.CavpotBatch()
-    b.n_struct, b.n_types, b.n_atoms, b.max_types, b.max_atoms, b.n_dens = S, T, A, 0, 0, int(rho.shape[0])
-    keep = dict(type_off=type_off, atom_off=atom_off, rc=rc, nrr=nrr, z=z, zc=zc, rmt=rmt, dens=dens, rk=rk, rho=rho, nx=nx,
-                alpha=alpha, nh=nh, slab=slab, esht=esht, nform=nform)
+    b.n_struct, b.n_types, b.n_atoms, b.max_types, b.max_atoms, b.n_dens = max(S, 0), T, A, 0, 0, int(rho.shape[0])
     for k, v in keep.items():
         setattr(b, k, v.ctypes.data)
-    out = dict(mtz2=np.zeros((S, 2)), npts=np.zeros(T, dtype=np.int32), pot=np.zeros((T, 421)))
+    out = dict(mtz2=np.zeros((max(S, 0), 2)), npts=np.zeros(T, dtype=np.int32), pot=np.zeros((T, 421)))
     r = _lib.CavpotResult()
     r.mtz, r.npts, r.pot, r.pot_stride = out["mtz2"].ctypes.data, out["npts"].ctypes.data, out["pot"].ctypes.data, 421
     if diagnostics:
         out.update(vh=np.zeros((T, 250)), vs=np.zeros((T, 250)), vmad=np.zeros((T, 250)), shell_ad=np.zeros((T, 30)),
                    shell_na=np.zeros((T, 30), dtype=np.int32), shell_ia=np.zeros((T, 30), dtype=np.int32),
-                   ncon=np.zeros(T, dtype=np.int32), stats=np.zeros((S, 4), dtype=np.int32))
+                   ncon=np.zeros(T, dtype=np.int32), stats=np.zeros((max(S, 0), 4), dtype=np.int32))
         for k in ("vh", "vs", "vmad", "shell_ad", "shell_na", "shell_ia", "ncon", "stats"):
             setattr(r, k, out[k].ctypes.data)
     _lib.check(_lib.load().phsh_b200_cavpot_batch_host(C.byref(b), C.byref(r), 0, int(device)))
     out["vhar"], out["vex"] = out["mtz2"][:, 0].copy(), out["mtz2"][:, 1].copy()
     out["mtz"] = out["vhar"] + out["vex"]
-    out["type_off"] = type_off
+    out["type_off"] = keep["type_off"]
     del out["mtz2"]
     return out
 
@@ -394,3 +411,11 @@ def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, 
                                                  enc(mufftin_file), enc(output_file), enc(info_file), C.byref(opts),
                                                  C.byref(mtz)))
     return float(mtz.value)
+
+
+def selftest_cavpot(n=1 << 22, seed=1, device=0):
+    """Mismatches (must be 0) of cavpot_kernel's table-driven division and mesh-index look-up against the IEEE division
+    and the threshold table, on ``n`` pseudo-random operands plus the doubles around every threshold."""
+    bad = C.c_ulonglong(0)
+    _lib.check(_lib.load().phsh_b200_selftest_cavpot(int(n), int(seed), C.byref(bad), int(device)))
+    return int(bad.value)

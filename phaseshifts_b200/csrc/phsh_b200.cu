@@ -4,7 +4,9 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
+#include <limits>
 #include <mutex>
+#include <cstdint>
 #include <vector>
 
 #include "phsh_common.h"

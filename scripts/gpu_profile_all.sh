@@ -1,6 +1,7 @@
 # Regenerates every artefact under profiles/ for the current tree (1 GPU), one ncu pass per call.
 # Usage: gpurun -- bash scripts/gpu_profile_all.sh 1   (tests, bench lines, launch list)
 #        gpurun -- bash scripts/gpu_profile_all.sh 2   (ncu --set full capture of the dominant kernel)
+#        gpurun -- bash scripts/gpu_profile_all.sh 3   (ncu --set full capture of cavpot_kernel on the C6 workload)
 set -x
 if [ "${1:-1}" = 1 ]; then
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.txt; cat gpurun_out/pytest_gpu.txt
@@ -11,6 +12,11 @@ CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final_launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 cut -c1-200 gpurun_out/final_bench_n1.json
+elif [ "$1" = 3 ]; then
+CMD3="python scripts/exp/cavpot_time.py 4096"
+$CMD3 > gpurun_out/cavpot_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:cavpot_kernel -s 1 -c 1 -o gpurun_out/final_prof_cavpot $CMD3 > gpurun_out/ncu_cavpot.log 2>&1
+tail -2 gpurun_out/ncu_cavpot.log | cut -c1-200; cat gpurun_out/cavpot_plain.log
 else
 CMD2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD2 > gpurun_out/ncu_plain2.log 2>&1 &&

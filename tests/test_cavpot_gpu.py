@@ -62,6 +62,15 @@ def test_rela_density_interpolation_on_the_gpu(re_case):
     assert o_nx < 250
 
 
+def test_table_driven_division_and_mesh_index_are_exact():
+    """cp_div (quotient from a tabulated correctly rounded reciprocal, two residual corrections) == IEEE division for all
+    748 x 2 mesh-difference divisors; cp_index_tab == its threshold table, whose entries were bisected on the host with
+    the very formula the oracle evaluates (INT(20*(ALOG(x)+8.8)+add))."""
+    from phaseshifts_b200 import api
+    assert api.selftest_cavpot(1 << 24, seed=3) == 0
+    assert api.selftest_cavpot(1 << 20, seed=11) == 0
+
+
 @pytest.mark.parametrize("nform", [2, 0, 1])
 def test_re_bulk_matches_oracle(re_case, nform):
     from oracle import cavpot_io as cio
