@@ -355,7 +355,7 @@ _CAVPOT_FIELDS = (("type_off", np.int32), ("atom_off", np.int32), ("rc", np.floa
                   ("nh", np.int32), ("slab", np.int32), ("esht", np.float64), ("nform", np.int32))
 
 
-def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
+def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=False):
     """The muffin-tin potential step of ``libphsh.cavpot`` (``libphsh.f:2070-2557``) for a batch of structures.
 
     ``structures``: sequence of dicts with ``spa`` (lattice constant, bohr), ``rc`` [3][3] (axis j = ``rc[j]``, in units of
@@ -363,6 +363,11 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
     ``dens`` [nr] (row of ``rho`` for each atom type), ``alpha``, ``nh``, ``nform`` and optionally ``slab`` / ``esht`` -- or the
     dict of flat arrays ``cavpot_pack`` makes of such a sequence (lengths in bohr), which skips the per-structure Python work.
     ``rho`` [n_dens][250], ``nx`` [n_dens]: the atomic charge densities on Loucks' mesh (``cavpot_rela_density``).
+
+    With ``on_device`` the inputs are uploaded once, the kernel runs on torch's current stream of CUDA device ``device``
+    and ``pot`` [T][422], ``npts`` [T], ``mtz``/``vhar``/``vex`` [S] come back as CUDA tensors -- ``pot``/``npts`` of an
+    NFORM=2 batch are exactly the ``pot``/``jri`` arguments of ``phsh_rel_batch`` (same grid, r*V, even row stride), so
+    structures -> potentials -> phase shifts chains on the device without a host round trip.
 
     Returns a dict: ``mtz`` [S] (VHAR+VEX, what ``cavpot`` returns for a bulk run), ``vhar``, ``vex`` [S], ``npts`` [T],
     ``pot`` [T][421], ``type_off`` [S+1]; with ``diagnostics`` also ``vh``, ``vs``, ``vmad`` [T][250], the neighbour shells
@@ -381,6 +386,10 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
     if nx.size != rho.shape[0]:
         raise ValueError("nx has %d entries for %d densities" % (nx.size, rho.shape[0]))
     keep.update(rho=rho, nx=nx)
+    if on_device:
+        if diagnostics:
+            raise ValueError("diagnostics are returned by the host entry point only")
+        return _cavpot_batch_device(keep, S, T, A, int(rho.shape[0]), int(device))
     b = _lib.CavpotBatch()
     b.n_struct, b.n_types, b.n_atoms, b.max_types, b.max_atoms, b.n_dens = max(S, 0), T, A, 0, 0, int(rho.shape[0])
     for k, v in keep.items():
@@ -400,6 +409,30 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0):
     out["type_off"] = keep["type_off"]
     del out["mtz2"]
     return out
+
+
+def _cavpot_batch_device(keep, S, T, A, n_dens, device):
+    import torch
+    dev = torch.device("cuda", device)
+    d = {k: torch.from_numpy(v).to(dev) for k, v in keep.items()}
+    to, ao = keep["type_off"], keep["atom_off"]
+    b = _lib.CavpotBatch()
+    b.n_struct, b.n_types, b.n_atoms, b.n_dens = S, T, A, n_dens
+    b.max_types = int(np.diff(to).max()) if S else 1
+    b.max_atoms = int(np.diff(ao).max()) if S else 1
+    for k, v in d.items():
+        setattr(b, k, v.data_ptr())
+    mtz = torch.zeros((S, 2), dtype=torch.float64, device=dev)
+    npts = torch.zeros(T, dtype=torch.int32, device=dev)
+    pot = torch.zeros((T, 422), dtype=torch.float64, device=dev)
+    r = _lib.CavpotResult()
+    r.mtz, r.npts, r.pot, r.pot_stride = mtz.data_ptr(), npts.data_ptr(), pot.data_ptr(), 422
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().phsh_b200_cavpot_batch_device(C.byref(b), C.byref(r), 0, C.c_void_p(stream)))
+        # the inputs must outlive the launch: keep them referenced by the result until the stream has consumed them
+    return dict(mtz=mtz[:, 0] + mtz[:, 1], vhar=mtz[:, 0], vex=mtz[:, 1], npts=npts, pot=pot, type_off=keep["type_off"],
+                _inputs=d)
 
 
 def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file, *, device=0):

@@ -89,6 +89,68 @@ def phsh_rel_sweep(pot, jri, energies_ryd, lmax, *, gather=True, compute=None, g
     return gather_blocks(t, P, group=group).cpu().numpy()
 
 
+def _gather_ragged(local, sizes, group=None):
+    """All-gather blocks whose row counts ``sizes[rank]`` every rank can work out from the (replicated) inputs."""
+    import torch
+    d = _dist()
+    rank, world = d.get_rank(group), d.get_world_size(group)
+    if local.shape[0] != sizes[rank]:
+        raise ValueError("rank %d holds %d rows, expected %d" % (rank, local.shape[0], sizes[rank]))
+    buf = local.new_zeros((max(max(sizes), 1),) + tuple(local.shape[1:]))
+    buf[: local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    d.all_gather(parts, buf, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+def cavpot_sweep(structures, rho, nx, *, gather=True, compute=None, group=None):
+    """Muffin-tin potentials of a list of structures sharded over the ranks of the current process group.
+
+    Structures are independent, so rank r of W owns ``shard_range(S, r, W)`` and there is no data-path collective.
+    ``compute(structures, rho, nx)`` defaults to ``api.cavpot_batch`` on GPU ``LOCAL_RANK`` (the CPU tests inject the
+    oracle).  With ``gather`` every rank returns ``dict(mtz [S], npts [T], pot [T][421], type_off [S+1])`` for the whole
+    list (the rows of atom types are ragged per structure; every rank derives the block sizes from the replicated
+    input); otherwise ``(local_result, (start, stop))``.
+    """
+    import torch
+    rank, world = rank_world()
+    S = len(structures)
+    a, b = shard_range(S, rank, world)
+    if compute is None:
+        from . import api
+        local_rank = int(os.environ.get("LOCAL_RANK", rank))
+
+        def compute(st, rho_, nx_):
+            return api.cavpot_batch(st, rho_, nx_, device=local_rank)
+    ntypes = np.array([len(np.asarray(st["nrr"]).reshape(-1)) for st in structures], dtype=np.int64)
+    type_off = np.concatenate([[0], np.cumsum(ntypes)]).astype(np.int32)
+    if b > a:
+        res = compute(list(structures[a:b]), rho, nx)
+        local = dict(mtz=np.asarray(res["mtz"], dtype=np.float64), npts=np.asarray(res["npts"], dtype=np.int32),
+                     pot=np.asarray(res["pot"], dtype=np.float64)[:, :421])
+    else:
+        local = dict(mtz=np.zeros(0), npts=np.zeros(0, dtype=np.int32), pot=np.zeros((0, 421)))
+    if not gather or world == 1:
+        if world == 1 and gather:
+            return dict(local, type_off=type_off)
+        return local, (a, b)
+    d = _dist()
+    dev = None
+    if d is not None and d.get_backend(group) == "nccl":
+        dev = int(os.environ.get("LOCAL_RANK", rank))
+    ranges = [shard_range(S, r, world) for r in range(world)]
+    s_sizes = [hi - lo for lo, hi in ranges]
+    t_sizes = [int(type_off[hi] - type_off[lo]) for lo, hi in ranges]
+    out = {}
+    for key, sizes in (("mtz", s_sizes), ("npts", t_sizes), ("pot", t_sizes)):
+        t = torch.from_numpy(np.ascontiguousarray(local[key]))
+        if dev is not None:
+            t = t.cuda(dev)
+        out[key] = _gather_ragged(t, sizes, group=group).cpu().numpy()
+    out["type_off"] = type_off
+    return out
+
+
 def phsh_rel_batch_multi(pot, jri, energies_ryd, lmax, *, devices=None, **kwargs):
     """Single-process variant: shard ``pot`` [P, J] (host array) over several GPUs of this process.
 

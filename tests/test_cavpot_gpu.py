@@ -160,6 +160,39 @@ def test_ragged_batch_of_perturbed_structures(re_case):
         assert np.array_equal(out["shell_na"][t0:t0 + c["nr"]], ref["na"])
 
 
+def test_structures_to_phase_shifts_on_the_device(re_case):
+    """cavpot_batch(on_device) hands `pot`/`npts` straight to phsh_rel_batch (same grid, r*V, even stride): geometry
+    variants -> muffin-tin potentials -> delta_l(E) without a host round trip; against the oracle chain to 1e-8 rad."""
+    import torch
+    from oracle import cavpot_io as cio, oracle as orc
+    from phaseshifts_b200 import api
+    cl, _, rho, nx = re_case
+    rng = np.random.default_rng(5)
+    cls = []
+    for s in range(6):
+        c = dict(cl)
+        c["rmt"] = np.round(cl["rmt"] * (1 + 0.08 * rng.uniform(-1, 1)), 4)
+        c["rk"] = cl["rk"] + np.round(0.01 * rng.normal(size=cl["rk"].shape), 4)
+        cls.append(c)
+    dev = api.cavpot_batch([_struct(c) for c in cls], rho, nx, on_device=True)
+    host = api.cavpot_batch([_struct(c) for c in cls], rho, nx)
+    assert dev["pot"].is_cuda and dev["pot"].shape == (12, 422)
+    assert np.array_equal(dev["pot"].cpu().numpy()[:, :421], host["pot"]) and np.array_equal(dev["npts"].cpu().numpy(), host["npts"])
+    assert np.array_equal(dev["mtz"].cpu().numpy(), host["mtz"])
+    g = api.rel_energy_grid(20.0, 5.0, 300.0)
+    delta = api.phsh_rel_batch(dev["pot"], dev["npts"], g["e_l"], 12, energies_l0=g["e_l0"], unwrap=True)
+    torch.cuda.synchronize()
+    delta = delta.cpu().numpy()
+    assert delta.shape == (12, 57, 13) and np.isfinite(delta).all()
+    for s, c in enumerate(cls):
+        ref = cio.cavpot(c, rho, nx, real32=False)
+        pot = np.zeros((2, 422))
+        pot[:, :421] = ref["v"][:, :421]
+        jf = orc.rel_batch(pot, ref["npts"], g["e_l0"], g["e_l"], lsm=12)["jf"]
+        want = np.stack([orc.conphas(x) for x in jf])
+        assert np.abs(delta[2 * s:2 * s + 2] - want).max() <= 1e-8
+
+
 def _values(path):
     lines = open(path).read().split("\n")
     blocks, i = [], 0

@@ -67,3 +67,65 @@ def test_two_rank_sweep_equals_single_rank(tmp_path, P, oracle):
         assert np.array_equal(np.load(tmp_path / ("full_%d.npy" % r)), ref)
         a, b = np.load(tmp_path / ("range_%d.npy" % r))
         assert np.array_equal(np.load(tmp_path / ("local_%d.npy" % r)), ref[a:b])
+
+
+def _cavpot_worker(rank, world, port, S, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from phaseshifts_b200 import distributed as D
+    structs, rho, nx = _cavpot_case(S)
+    full = D.cavpot_sweep(structs, rho, nx, compute=_oracle_cavpot)
+    local, (a, b) = D.cavpot_sweep(structs, rho, nx, compute=_oracle_cavpot, gather=False)
+    np.savez(os.path.join(out_dir, "cav_%d.npz" % rank), mtz=full["mtz"], npts=full["npts"], pot=full["pot"],
+             type_off=full["type_off"], lmtz=local["mtz"], rng=np.array([a, b]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _cavpot_case(S):
+    """S ragged structures (1 or 2 atom types) with a synthetic density; NH small to keep the oracle quick."""
+    rng = np.random.default_rng(3)
+    x = np.exp(-8.8 + 0.05 * np.arange(250))
+    rho = (4 * 8.0 ** 3 * x * x * np.exp(-2 * 2.0 * x))[None, :] * 10.0   # 4 pi r^2 times a 1s-like density, 10 electrons
+    nx = np.array([250], dtype=np.int32)
+    structs = []
+    for s in range(S):
+        two = s % 3 != 0
+        structs.append(dict(spa=5.0 + 0.1 * s, rc=np.eye(3), nrr=[1, 1] if two else [1], z=[10.0, 10.0] if two else [10.0],
+                            zc=[0.0, 0.0] if two else [0.0], rmt=[2.0, 2.1] if two else [2.3],
+                            rk=[[0, 0, 0], [0.5, 0.5, 0.5]] if two else [[0, 0, 0]], dens=[0, 0] if two else [0],
+                            alpha=0.7, nh=3, nform=2))
+    return structs, rho, nx
+
+
+def _oracle_cavpot(structs, rho, nx):
+    from oracle import cavpot_io as cio
+    mtz, npts, pot = [], [], []
+    for st in structs:
+        nr = len(st["nrr"])
+        c = dict(spa=st["spa"], rc=np.asarray(st["rc"], dtype=float), nr=nr, nrr=np.asarray(st["nrr"], dtype=np.int32),
+                 z=np.asarray(st["z"], dtype=float), zc=np.asarray(st["zc"], dtype=float), rmt=np.asarray(st["rmt"], dtype=float),
+                 rk=np.asarray(st["rk"], dtype=float), nform=st["nform"], alpha=st["alpha"], nh=st["nh"])
+        d = np.asarray(st["dens"])
+        r = cio.cavpot(c, np.asarray(rho)[d], np.asarray(nx)[d], real32=False)
+        mtz.append(r["mtz"])
+        npts += list(r["npts"])
+        pot += [r["v"][i, :421] for i in range(nr)]
+    return dict(mtz=np.array(mtz), npts=np.array(npts, dtype=np.int32), pot=np.array(pot).reshape(-1, 421))
+
+
+@pytest.mark.parametrize("S", [5, 2])
+def test_two_rank_cavpot_sweep_equals_single_rank(tmp_path, S):
+    world = 2
+    mp.spawn(_cavpot_worker, args=(world, _free_port(), S, str(tmp_path)), nprocs=world, join=True)
+    structs, rho, nx = _cavpot_case(S)
+    ref = _oracle_cavpot(structs, rho, nx)
+    for r in range(world):
+        z = np.load(tmp_path / ("cav_%d.npz" % r))
+        assert np.array_equal(z["mtz"], ref["mtz"]) and np.array_equal(z["npts"], ref["npts"])
+        assert np.array_equal(z["pot"], ref["pot"]) and z["type_off"][-1] == ref["pot"].shape[0]
+        a, b = z["rng"]
+        assert np.array_equal(z["lmtz"], ref["mtz"][a:b])
