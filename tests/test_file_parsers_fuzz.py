@@ -123,3 +123,58 @@ def test_absurd_headers_are_rejected_not_allocated(tmp_path):
     from phaseshifts_b200.conphas import Conphas
     with pytest.raises((PhshB200Error, IndexError)):
         Conphas(input_files=[str(ph)], output_file=str(tmp_path / "o"), lmax=2).calculate()
+
+
+CLU = os.path.join(ROOT, "tests", "golden", "Re0001", "cluster_Re_bulk.i")
+ATO = os.path.join(ROOT, "tests", "golden", "Re0001", "atomic_Re.i")
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(seed=st.integers(0, 10 ** 9), mode=st.integers(0, 3), which=st.sampled_from(["cluster", "atomic"]))
+def test_cavpot_file_mutations(tmp_path, seed, mode, which):
+    """cluster.i / atomic.i readers of phsh_b200_cavpot_file: mutated inputs end in an error code (or ENODEV at the first
+    device call of a file that still parses), never in a crash."""
+    from phaseshifts_b200 import api
+    c, a = tmp_path / "c.i", tmp_path / "a.i"
+    c.write_text(_mutate(open(CLU).read(), seed, mode) if which == "cluster" else open(CLU).read())
+    a.write_text(_mutate(open(ATO).read(), seed, mode) if which == "atomic" else open(ATO).read())
+    _call(api.cavpot_file, "", 0, str(a), str(c), str(tmp_path / "m.d"), str(tmp_path / "o.i"), str(tmp_path / "info.txt"))
+    _call(api.cavpot_file, "-1.5", 1, str(a), str(c), str(tmp_path / "m.d"), str(tmp_path / "o.i"), "")
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(body=_text)
+def test_cavpot_file_on_garbage(tmp_path, body):
+    from phaseshifts_b200 import api
+    g = tmp_path / "g.i"
+    g.write_text(body)
+    out = [str(tmp_path / n) for n in ("m.d", "o.i", "info.txt")]
+    _call(api.cavpot_file, "", 0, ATO, str(g), *out)
+    _call(api.cavpot_file, "", 0, str(g), CLU, *out)
+
+
+def test_cavpot_batch_argument_checks():
+    """Host-side validation of phsh_b200_cavpot_batch_host happens before any device call."""
+    import numpy as np
+    from phaseshifts_b200 import api, PhshB200Error
+    st_ok = dict(spa=5.0, rc=np.eye(3), nrr=[1], z=[10.0], zc=[0.0], rmt=[2.0], rk=[[0, 0, 0]], dens=[0], alpha=0.7, nh=4, nform=2)
+    rho, nx = np.ones((1, 250)), [250]
+
+    def code(st, rho=rho, nx=nx):
+        with pytest.raises(PhshB200Error) as e:
+            api.cavpot_batch([st], rho, nx)
+        return e.value.code
+
+    from phaseshifts_b200 import _lib
+    if _lib.device_count() == 0:
+        assert code(st_ok) in (-2, -3)                               # no GPU here: everything else was accepted
+    assert code(dict(st_ok, rmt=[0.0])) == -1
+    assert code(dict(st_ok, rmt=[40.0])) == -1                       # off Loucks' mesh
+    assert code(dict(st_ok, dens=[3])) == -1
+    assert code(dict(st_ok, nform=5)) == -1
+    assert code(dict(st_ok, nh=100000)) == -1
+    assert code(dict(st_ok, nrr=[2])) == -1                          # atoms do not add up
+    assert code(dict(st_ok, spa=1e-4)) == -1                         # neighbour search would visit ~1e17 cells
+    assert code(st_ok, nx=[1]) == -1
+    with pytest.raises(ValueError):
+        api.cavpot_batch([dict(st_ok, z=[1.0, 2.0])], rho, nx)
