@@ -4,6 +4,8 @@
 1. Re0001/*: copies of the reference's own fixture files tests/Re0001/{mufftin_Re_slab.d, dataph_Re.d,
    leedph_Re.d, cluster_Re_*.i, atomic_Re.i, mufftin_Re_bulk.d} (data, not source).  cluster_Re_bulk.i + atomic_Re.i ->
    mufftin_Re_bulk.d is the reference's input/output pair of the muffin-tin potential step (CAVPOT).
+   examples/*: phaseshifts/examples/input_files/{cluster,atomic}_C6Ni6.i -- a real 8-type / 20-atom NFORM=1 input of the
+   muffin-tin potential step (no reference output exists for it; used GPU-vs-oracle only).
 2. conphas/*: outputs of the reference's *own* Python ``phaseshifts.conphas.Conphas`` (imported from
    /root/reference with a stub ``libphsh``) run on
      - Re_A.ph   : the first section of the phasout the oracle (FP32-as-written) writes for the Re fixture,
@@ -41,6 +43,11 @@ def main():
     for f in ("mufftin_Re_slab.d", "dataph_Re.d", "leedph_Re.d", "cluster_Re_slab.i", "cluster_Re_bulk.i", "at_Re.i",
               "atomic_Re.i", "mufftin_Re_bulk.d"):
         shutil.copyfile(os.path.join(REF, "tests", "Re0001", f), os.path.join(re_dir, f))
+
+    ex_dir = os.path.join(HERE, "examples")
+    os.makedirs(ex_dir, exist_ok=True)
+    for f in ("cluster_C6Ni6.i", "atomic_C6Ni6.i"):
+        shutil.copyfile(os.path.join(REF, "phaseshifts", "examples", "input_files", f), os.path.join(ex_dir, f))
 
     from oracle import fortran_io as fio
     out = os.path.join(HERE, "conphas")

@@ -193,6 +193,38 @@ def test_structures_to_phase_shifts_on_the_device(re_case):
         assert np.abs(delta[2 * s:2 * s + 2] - want).max() <= 1e-8
 
 
+def test_real_eight_type_input_nform1(tmp_path):
+    """phaseshifts/examples/input_files/cluster_C6Ni6.i: 8 atom types, 20 atoms, NFORM=1 (Williams), 6 different charge
+    densities -- batch entry point and file interface against the oracle."""
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    ex = os.path.join(HERE, "golden", "examples")
+    cl = cio.read_cluster(os.path.join(ex, "cluster_C6Ni6.i"), real32=False)
+    assert cl["nr"] == 8 and len(cl["rk"]) == 20 and cl["nform"] == 1
+    blocks = cio.read_atomic(os.path.join(ex, "atomic_C6Ni6.i"), cl["nr"], real32=False)
+    rho = np.zeros((8, 250))
+    nx = np.zeros(8, dtype=np.int32)
+    for i, b in enumerate(blocks):
+        rho[i], nx[i] = cio.rela_density(b, real32=False)
+        g_rho, g_nx = api.cavpot_rela_density(b["rmin"], b["rmax"], b["rs"], b["iprint"])
+        assert g_nx == nx[i] and np.array_equal(g_rho, rho[i])
+    ref = cio.cavpot(cl, rho, nx, real32=False)
+    out = api.cavpot_batch([_struct(cl)], rho, nx, diagnostics=True)
+    _check(out, 0, ref, 8)
+    assert list(out["stats"][0][:2]) == [ref["nint"], ref["npoint"]] and abs(out["mtz"][0] - ref["mtz"]) < 1e-12
+    assert np.array_equal(out["shell_na"], ref["na"]) and np.array_equal(out["shell_ia"], ref["ia"])
+    g = [str(tmp_path / n) for n in ("g.d", "g.i", "g.txt")]
+    o = [str(tmp_path / n) for n in ("o.d", "o.i", "o.txt")]
+    api.cavpot_file("", 0, os.path.join(ex, "atomic_C6Ni6.i"), os.path.join(ex, "cluster_C6Ni6.i"), *g)
+    cio.cavpot_file("", 0, os.path.join(ex, "atomic_C6Ni6.i"), os.path.join(ex, "cluster_C6Ni6.i"), *o, real32=False)
+    la, lb = open(g[0]).read().split("\n"), open(o[0]).read().split("\n")
+    assert len(la) == len(lb) and la[0] == " &NL2 NRR= 8 &end" and la[1].startswith(" &NL16 Z=")
+    assert sum(x != y for x, y in zip(la, lb)) <= 2
+    # and the Williams phase-shift program reads what we wrote
+    api.phsh_wil_file(g[0], str(tmp_path / "phasout"), str(tmp_path / "dataph"), str(tmp_path / "zph"))
+    assert len(open(tmp_path / "phasout").read().splitlines()) > 8
+
+
 def _values(path):
     lines = open(path).read().split("\n")
     blocks, i = [], 0

@@ -122,3 +122,26 @@ def test_asbuilt_nbr_leaves_the_type_loop_early():
     assert list(good["ncon"]) == [30, 30]
     assert bad["na"][1].sum() < good["na"][1].sum()
     assert np.abs(bad["v"][1, :321] - good["v"][1, :321]).max() > 1e-3
+
+
+REF_EX = os.path.join(os.environ.get("PHASESHIFTS_REFERENCE", "/root/reference"), "phaseshifts", "examples", "input_files")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EX), reason="reference checkout not available")
+@pytest.mark.parametrize("stem", ["", "_C6Ni6", "_Ni", "_Re", "_Re_slab:_Re", "_Rh", "_W", "_W_slab:_W", "_pseudoNi"])
+def test_oracle_runs_on_the_reference_example_inputs(stem):
+    """Every well-formed cluster/atomic pair among the reference's example inputs (2-8 atom types, NFORM 1 and 2, bulk and
+    20-bohr vacuum cells): finite potentials, a negative muffin-tin zero, interstitial sample points found."""
+    cs, _, as_ = stem.partition(":")
+    cl = cio.read_cluster(os.path.join(REF_EX, "cluster%s.i" % cs), real32=False)
+    blocks = cio.read_atomic(os.path.join(REF_EX, "atomic%s.i" % (as_ or cs)), cl["nr"], real32=False)
+    rho = np.zeros((cl["nr"], 250))
+    nx = np.zeros(cl["nr"], dtype=np.int32)
+    for i, b in enumerate(blocks):
+        rho[i], nx[i] = cio.rela_density(b, real32=False)
+    r = cio.cavpot(cl, rho, nx, real32=False)
+    assert r["nint"] > 0 and r["npoint"] == cl["nh"] ** 3 and -3.0 < r["mtz"] < 0.0
+    for i in range(cl["nr"]):
+        v = r["v"][i, :r["npts"][i]]
+        assert np.isfinite(v).all() and (v[:5] < 0).all()
+        assert abs(v[0] / (-2.0 * cl["z"][i])) - 1.0 < 1e-2      # r*V -> -2Z at the origin
