@@ -7,6 +7,7 @@
 // byte-for-byte where a downstream reader exists (`phasout`, parsed by phaseshifts/conphas.py:171-257).
 // All numerics happen on the GPU through phsh_b200_*_batch_host; nothing is computed here.
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -35,23 +36,38 @@ std::string pad(const std::string& s, size_t n) {
 
 // Fw.d / Ew.d / Dw.d input editing of one field (BLANK=NULL): blanks ignored, D exponent, implied decimals
 bool fread_field(const std::string& field, int d, double* out) {
-    std::string s;
-    for (char c : field)
-        if (c != ' ' && c != '\t') s.push_back(c == 'D' || c == 'd' ? 'E' : c);
-    if (s.empty()) {
+    char s[96];
+    size_t n = 0;
+    bool has_point = false, in_exp = false;
+    for (char c : field) {
+        if (c == ' ' || c == '\t') continue;
+        if (n + 2 >= sizeof s) return false;
+        if (c == 'D' || c == 'd' || c == 'e') c = 'E';
+        // exponent without a letter: 1.5+03
+        if ((c == '+' || c == '-') && n > 0 && s[n - 1] != 'E' && !in_exp) {
+            s[n++] = 'E';
+            in_exp = true;
+        }
+        if (c == 'E') in_exp = true;
+        if (c == '.' && !in_exp) has_point = true;
+        s[n++] = c;
+    }
+    if (n == 0) {
         *out = 0.0;
         return true;
     }
-    for (size_t i = 1; i < s.size(); ++i)  // exponent without a letter: 1.5+03
-        if ((s[i] == '+' || s[i] == '-') && s[i - 1] != 'E' && s[i - 1] != 'e') {
-            s.insert(i, "E");
-            break;
-        }
-    char* end = nullptr;
-    const double v = strtod(s.c_str(), &end);
-    if (end == s.c_str() || *end != '\0') return false;
-    const std::string mant = s.substr(0, s.find_first_of("Ee"));
-    *out = (mant.find('.') == std::string::npos) ? v * std::pow(10.0, -d) : v;
+    const char* b = s + (s[0] == '+' ? 1 : 0);  // from_chars takes no leading '+'
+    double v = 0.0;
+    const auto r = std::from_chars(b, s + n, v);
+    if (r.ec == std::errc::result_out_of_range) {  // strtod's behaviour: +-HUGE_VAL or 0
+        s[n] = '\0';
+        char* end = nullptr;
+        v = strtod(s, &end);
+        if (end != s + n) return false;
+    } else if (r.ec != std::errc() || r.ptr != s + n || b == s + n) {
+        return false;
+    }
+    *out = has_point ? v : v * std::pow(10.0, -d);
     return true;
 }
 
@@ -71,19 +87,43 @@ bool iread_field(const std::string& field, int* out) {
 }
 
 // ---------------------------------------------------------------- Fortran formatted output
+// shortest-path conversions: std::to_chars with an explicit precision prints exactly what printf's %.*f / %.*e
+// print (correctly rounded decimal of the binary value) at a fraction of the cost
+inline int fixed_chars(char* buf, size_t cap, double x, int d) {
+    const auto r = std::to_chars(buf, buf + cap - 1, x, std::chars_format::fixed, d);
+    if (r.ec != std::errc()) return snprintf(buf, cap, "%.*f", d, x);
+    *r.ptr = '\0';
+    return static_cast<int>(r.ptr - buf);
+}
+inline int sci_chars(char* buf, size_t cap, double x, int d) {
+    const auto r = std::to_chars(buf, buf + cap - 1, x, std::chars_format::scientific, d);
+    if (r.ec != std::errc()) return snprintf(buf, cap, "%.*e", d, x);
+    *r.ptr = '\0';
+    return static_cast<int>(r.ptr - buf);
+}
+
 // Fw.d as gfortran writes it: optional leading zero dropped when the field is too narrow, asterisks on overflow
 std::string ffmt(double x, int w, int d) {
     char buf[512];
-    snprintf(buf, sizeof buf, "%.*f", d, x);
-    std::string s = buf;
-    if (static_cast<int>(s.size()) > w) {
-        if (s.compare(0, 2, "0.") == 0)
-            s.erase(0, 1);
-        else if (s.compare(0, 3, "-0.") == 0)
-            s.erase(1, 1);
+    const int n = fixed_chars(buf, sizeof buf, x, d);
+    const char* p = buf;
+    int len = n;
+    char tmp[512];
+    if (len > w) {
+        if (buf[0] == '0' && buf[1] == '.') {
+            p = buf + 1;
+            --len;
+        } else if (buf[0] == '-' && buf[1] == '0' && buf[2] == '.') {
+            tmp[0] = '-';
+            memcpy(tmp + 1, buf + 2, n - 1);
+            p = tmp;
+            --len;
+        }
     }
-    if (static_cast<int>(s.size()) > w) return std::string(w, '*');
-    return std::string(w - s.size(), ' ') + s;
+    if (len > w) return std::string(w, '*');
+    std::string s(w, ' ');
+    memcpy(&s[w - len], p, len);
+    return s;
 }
 
 // Dw.d / Ew.d: 0.ddddD+ee
@@ -93,15 +133,17 @@ std::string dfmt(double x, int w, int d, char letter) {
         body = "0." + std::string(d, '0') + letter + "+00";
     } else {
         char buf[128];
-        snprintf(buf, sizeof buf, "%.*e", d - 1, std::fabs(x));
-        std::string e = buf;
-        const size_t pe = e.find('e');
-        std::string mant = e.substr(0, pe);
-        int ex = atoi(e.c_str() + pe + 1) + 1;
-        mant.erase(std::remove(mant.begin(), mant.end(), '.'), mant.end());
+        sci_chars(buf, sizeof buf, std::fabs(x), d - 1);
+        const char* pe = strchr(buf, 'e');
+        const int ex = atoi(pe + 1) + 1;
+        body.reserve(w + 4);
+        if (x < 0) body.push_back('-');
+        body += "0.";
+        body.push_back(buf[0]);
+        if (d > 1) body.append(buf + 2, pe - (buf + 2));
         char eb[16];
         snprintf(eb, sizeof eb, "%c%c%02d", letter, ex >= 0 ? '+' : '-', std::abs(ex));
-        body = std::string(x < 0 ? "-" : "") + "0." + mant + eb;
+        body += eb;
     }
     if (static_cast<int>(body.size()) > w) {
         if (body.compare(0, 2, "0.") == 0)
@@ -113,7 +155,9 @@ std::string dfmt(double x, int w, int d, char letter) {
     return std::string(w - body.size(), ' ') + body;
 }
 
-// gfortran list-directed REAL(4) / REAL(8) field, leading separator blank included
+// gfortran list-directed REAL(4) / REAL(8) field, leading separator blank included.  One conversion: the d
+// significant digits of the E form are also the digits of the F form (same value, same number of significant
+// digits, the exponent taken after rounding), so the F form is assembled from them.
 std::string list_real(double x, int kind) {
     const int w = kind == 4 ? 16 : 25, d = kind == 4 ? 9 : 17, n = kind == 4 ? 4 : 5;
     char buf[128];
@@ -122,16 +166,29 @@ std::string list_real(double x, int kind) {
         std::string b = buf;
         return " " + std::string(w - n - b.size(), ' ') + b + std::string(n, ' ');
     }
-    snprintf(buf, sizeof buf, "%.*e", d - 1, x);
-    const int ex = atoi(strchr(buf, 'e') + 1);
+    sci_chars(buf, sizeof buf, x, d - 1);
+    char* pe = strchr(buf, 'e');
+    const int ex = atoi(pe + 1);
     const int k = ex + 1;
     if (k >= 0 && k <= d) {
-        snprintf(buf, sizeof buf, "%.*f", d - k, x);
-        std::string b = buf;
+        const bool neg = buf[0] == '-';
+        const char* m = buf + (neg ? 1 : 0);  // "D.DDDD..."
+        char digits[32];
+        digits[0] = m[0];
+        memcpy(digits + 1, m + 2, d - 1);
+        std::string b;
+        b.reserve(w);
+        if (neg) b.push_back('-');
+        if (k == 0)
+            b.push_back('0');
+        else
+            b.append(digits, k);
+        b.push_back('.');
+        b.append(digits + k, d - k);
         if (static_cast<int>(b.size()) > w - n) b = b.substr(0, w - n);
         return " " + std::string(w - n - b.size(), ' ') + b + std::string(n, ' ');
     }
-    std::string m(buf, strchr(buf, 'e') - buf);
+    std::string m(buf, pe - buf);
     char eb[16];
     snprintf(eb, sizeof eb, "E%c%0*d", ex >= 0 ? '+' : '-', n - 2, std::abs(ex));
     std::string b = m + eb;
@@ -364,12 +421,14 @@ static int phsh_b200_rel_file_impl(const char* mufftin, const char* phasout, con
                 fp.put(rec + "\n");
             }
         }
+        std::vector<std::string> etxt(b.n);  // the energy column repeats for every l
+        for (int ie = 0; ie < b.n; ++ie) etxt[ie] = list_real(b.e_ev[ie], 8);
         for (int kk = 0; kk < 8; ++kk) {  // nl=8 plotted phase shifts (libphsh.f:4707-4716)
             snprintf(t, sizeof t, "\"L=%2d\n", kk);
             fd.put(t);
             for (int ie = 0; ie < b.n; ++ie) {
                 const double v = kk < L1 ? jf[bi][static_cast<size_t>(ie) * L1 + kk] : 0.0;
-                fd.put(list_real(b.e_ev[ie], 8) + list_real(static_cast<double>(static_cast<float>(v)), 4) + "\n");
+                fd.put(etxt[ie] + list_real(static_cast<double>(static_cast<float>(v)), 4) + "\n");
             }
             fd.put("\n");
         }
