@@ -160,6 +160,41 @@ def test_ragged_batch_of_perturbed_structures(re_case):
         assert np.array_equal(out["shell_na"][t0:t0 + c["nr"]], ref["na"])
 
 
+def test_neighbour_shells_of_random_and_nearly_degenerate_cells(re_case):
+    """NBR in isolation: 240 random cells (skewed axes, 1-4 atoms of 1-3 types) whose atoms sit on symmetric positions plus
+    offsets of 1e-5 .. 3e-4 lattice units, i.e. shell distances that differ by about the 1e-4 tolerance of the reference's
+    ordered scan.  The GPU's warp-parallel scan (with its unordered pre-pass that discards far candidates) must end
+    with exactly the oracle's lists: same distances bit for bit, same counts, same types."""
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    cl, _, rho0, nx0 = re_case
+    rng = np.random.default_rng(2024)
+    sym = np.array([[0, 0, 0], [0.5, 0.5, 0.5], [0.5, 0.5, 0.0], [0.5, 0.0, 0.5], [0.0, 0.5, 0.5], [1 / 3, 2 / 3, 0.5],
+                    [0.25, 0.25, 0.25], [0.75, 0.25, 0.5]])
+    cells = [np.eye(3), np.array([[0.5, 0.866, 0.0], [0.5, -0.866, 0.0], [0.0, 0.0, 1.6]]),
+             np.array([[0.0, 0.5, 0.5], [0.5, 0.0, 0.5], [0.5, 0.5, 0.0]]), np.array([[1.0, 0.0, 0.0], [0.3, 0.9, 0.0], [0.1, 0.2, 1.3]])]
+    structs, cls = [], []
+    for s in range(240):
+        nr = int(rng.integers(1, 4))
+        nrr = rng.integers(1, 3, size=nr).astype(np.int32)
+        n = int(nrr.sum())
+        pos = sym[rng.choice(len(sym), size=n, replace=False)].copy()
+        pos += rng.choice([0.0, 1e-5, 5e-5, 1e-4, 3e-4], size=pos.shape) * rng.choice([-1.0, 1.0], size=pos.shape)
+        rc = cells[s % 4] * (1.0 + rng.choice([0.0, 1e-5, 1e-4]) * rng.normal(size=(3, 3)) * (s % 3 == 0))
+        c = dict(spa=float(rng.uniform(4.0, 9.0)), rc=rc, nr=nr, nrr=nrr, z=np.full(nr, 75.0), zc=np.zeros(nr),
+                 rmt=np.full(nr, 1.2), rk=pos, nform=2, alpha=0.7, nh=2)
+        cls.append(c)
+        structs.append(_struct(c, dens=np.zeros(nr, dtype=np.int32)))
+    out = api.cavpot_batch(structs, rho0[:1], nx0[:1], diagnostics=True)
+    for s, c in enumerate(cls):
+        ref = cio.cavpot(c, np.repeat(rho0[:1], c["nr"], axis=0), np.repeat(nx0[:1], c["nr"]), real32=False)
+        t0 = out["type_off"][s]
+        sl = slice(t0, t0 + c["nr"])
+        assert np.array_equal(out["ncon"][sl], ref["ncon"]), s
+        assert np.array_equal(out["shell_na"][sl], ref["na"]) and np.array_equal(out["shell_ia"][sl], ref["ia"]), s
+        assert np.array_equal(out["shell_ad"][sl], ref["ad"]), s
+
+
 def test_structures_to_phase_shifts_on_the_device(re_case):
     """cavpot_batch(on_device) hands `pot`/`npts` straight to phsh_rel_batch (same grid, r*V, even stride): geometry
     variants -> muffin-tin potentials -> delta_l(E) without a host round trip; against the oracle chain to 1e-8 rad."""
