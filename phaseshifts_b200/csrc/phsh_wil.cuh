@@ -124,6 +124,18 @@ __device__ __forceinline__ double div_by_0p75(double x) {
     return __fma_rn(r, c, q0);
 }
 
+// The same quotient with the range check deferred: the three-instruction sequence always runs, and the biased
+// exponent's distance from the window is folded into `worst` (integer pipe, no branch).  A caller that finds
+// worst > 1926 afterwards discards what it computed and repeats it with the IEEE division.
+__device__ __forceinline__ double div_by_0p75_tracked(double x, unsigned& worst) {
+    const unsigned e = (static_cast<unsigned>(__double2hiint(x)) >> 20) & 0x7ffu;
+    worst = max(worst, e - 93u);
+    const double c = 1.3333333333333333;
+    const double q0 = __dmul_rn(x, c);
+    const double r = __fma_rn(-0.75, q0, x);
+    return __fma_rn(r, c, q0);
+}
+
 __global__ void div075_selftest_kernel(unsigned long long seed, long n, unsigned long long* mismatches) {
     const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -139,19 +151,26 @@ __global__ void div075_selftest_kernel(unsigned long long seed, long n, unsigned
     const double a = div_by_0p75(x), b = __ddiv_rn(x, 0.75);
     const bool same = (__double_as_longlong(a) == __double_as_longlong(b)) || (a != a && b != b);
     if (!same) atomicAdd(mismatches, 1ULL);
+    // deferred check: whenever the recorded exponent distance stays inside the window the quotient is the IEEE one
+    unsigned worst = 0u;
+    const double t = div_by_0p75_tracked(x, worst);
+    if (worst <= 1926u && __double_as_longlong(t) != __double_as_longlong(b)) atomicAdd(mismatches, 1ULL);
 }
 
 // One Hamming step (phsh2.f:549-575) for the (P_l, Q_l) pair; slot PH is IP1-1.
-template <int PH>
+template <int PH, bool EXACT>
 __device__ __forceinline__ void hamming_step(double (&yP)[4], double (&yQ)[4], double (&fP)[4], double (&fQ)[4],
-                                             double& eP, double& eQ, double VME, double Ri, double T1, double FLP1) {
+                                             double& eP, double& eQ, double VME, double Ri, double T1, double FLP1,
+                                             unsigned& worst) {
     using M = RMath<double>;
     constexpr int ip1 = PH, im2 = (PH + 1) % 4, im1 = (PH + 2) % 4, ip0 = (PH + 3) % 4;
     const double cmod = static_cast<double>(0.925619835f), cfin = static_cast<double>(.743801653E-1f);
     // products by 2.0 and 0.125 are exact, so fusing them into the following add/sub rounds identically
-    fP[im2] = M::add(yP[ip1], div_by_0p75(__fma_rn(2.0, M::add(fP[ip0], fP[im2]), -fP[im1])));
+    const double xP = __fma_rn(2.0, M::add(fP[ip0], fP[im2]), -fP[im1]);
+    const double xQ = __fma_rn(2.0, M::add(fQ[ip0], fQ[im2]), -fQ[im1]);
+    fP[im2] = M::add(yP[ip1], EXACT ? __ddiv_rn(xP, 0.75) : div_by_0p75_tracked(xP, worst));
     yP[ip1] = M::sub(fP[im2], M::mul(cmod, eP));
-    fQ[im2] = M::add(yQ[ip1], div_by_0p75(__fma_rn(2.0, M::add(fQ[ip0], fQ[im2]), -fQ[im1])));
+    fQ[im2] = M::add(yQ[ip1], EXACT ? __ddiv_rn(xQ, 0.75) : div_by_0p75_tracked(xQ, worst));
     yQ[ip1] = M::sub(fQ[im2], M::mul(cmod, eQ));
     fP[ip1] = M::mul(M::add(M::mul(FLP1, yP[ip1]), M::mul(Ri, yQ[ip1])), T1);
     fQ[ip1] = M::mul(M::sub(M::mul(VME, yP[ip1]), M::mul(FLP1, yQ[ip1])), T1);
@@ -170,13 +189,13 @@ __device__ __forceinline__ void hamming_step(double (&yP)[4], double (&yQ)[4], d
 // grid.x = P * chunks; dyn smem: RS ZS stage_r stage_z [rpad] + R V T1 [NR+2] doubles + 16 B + IV[NR+2] ints
 // raw[(p*NE+ie)*NL + l] = atan(-|E|^(l+1/2) S/C)
 #ifndef PHSH_WIL_MINB
-#define PHSH_WIL_MINB 6
+#define PHSH_WIL_MINB 7
 #endif
 __global__ void __launch_bounds__(128, PHSH_WIL_MINB)
     wil_integrate_kernel(const double* __restrict__ rs_g, const double* __restrict__ zs_g, long stride,
                          const int* __restrict__ nrows_arr, const double* __restrict__ z_arr,
                          const double* __restrict__ rt_arr, const double* __restrict__ e_arr, int NE, int NL, int NR,
-                         int chunks, int rpad, double* __restrict__ raw) {
+                         int chunks, int rpad, int first_pass, double* __restrict__ raw) {
     using M = RMath<double>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* RS = reinterpret_cast<double*>(smem_raw);  // 1-based: RS[i] = table row i  (RS[0] unused)
@@ -284,12 +303,15 @@ __global__ void __launch_bounds__(128, PHSH_WIL_MINB)
         const int TLP1s = 2 * LP1;
         const double FLP1 = static_cast<double>(LP1);
         double yP[4], yQ[4], fP[4], fQ[4];
+        A1 = M::div(A1, static_cast<double>(2 * LP1 - 1));
+        // pass 0 divides by 0.75 with the three-instruction sequence and only records whether an operand ever left
+        // its validity window; if one did (never for a physical potential), pass 1 repeats this l with IEEE divisions
+        for (int pass = first_pass; pass < 2; ++pass) {
         // S10: power series about the origin at grid points 2..4 (slots 1..3); slot 0 is r=0
         yP[0] = 0.0;
         yQ[0] = 0.0;
         fP[0] = 0.0;
         fQ[0] = 0.0;
-        A1 = M::div(A1, static_cast<double>(2 * LP1 - 1));
         double Ak = A1;
         double Bk = M::div(M::mul(-Z, A1), static_cast<double>(LP1));
         double TR[4];
@@ -321,19 +343,32 @@ __global__ void __launch_bounds__(128, PHSH_WIL_MINB)
         // S5: Hamming's method, I = 5..NR; IP1-1 = (I-1)%4
         double eP = 0.0, eQ = 0.0;
         int I = 5;
-#define PHSH_HSTEP(PH)                                                                                \
-    {                                                                                                 \
-        const double Ri = R[I];                                                                       \
-        hamming_step<PH>(yP, yQ, fP, fQ, eP, eQ, M::mul(M::sub(V[I], E), Ri), Ri, T1s[I], FLP1);      \
-        if (++I > NR) break;                                                                          \
+        unsigned worst = 0u;
+#define PHSH_HSTEP(PH, EX)                                                                                    \
+    {                                                                                                         \
+        const double Ri = R[I];                                                                               \
+        hamming_step<PH, EX>(yP, yQ, fP, fQ, eP, eQ, M::mul(M::sub(V[I], E), Ri), Ri, T1s[I], FLP1, worst);   \
+        if (++I > NR) break;                                                                                  \
     }
-        for (;;) {
-            PHSH_HSTEP(0)
-            PHSH_HSTEP(1)
-            PHSH_HSTEP(2)
-            PHSH_HSTEP(3)
+        if (pass == 0) {
+            for (;;) {
+                PHSH_HSTEP(0, false)
+                PHSH_HSTEP(1, false)
+                PHSH_HSTEP(2, false)
+                PHSH_HSTEP(3, false)
+            }
+            if (worst <= 1926u) break;  // every operand was inside [2^-930, 2^+996]: the quotients are the IEEE ones
+        } else {
+#pragma unroll 1
+            for (;;) {
+                PHSH_HSTEP(0, true)
+                PHSH_HSTEP(1, true)
+                PHSH_HSTEP(2, true)
+                PHSH_HSTEP(3, true)
+            }
         }
 #undef PHSH_HSTEP
+        }  // pass
         const int il = (NR - 1) % 4;  // ILST-1
         const double yPl = il == 0 ? yP[0] : il == 1 ? yP[1] : il == 2 ? yP[2] : yP[3];
         const double yQl = il == 0 ? yQ[0] : il == 1 ? yQ[1] : il == 2 ? yQ[2] : yQ[3];

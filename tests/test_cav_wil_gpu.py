@@ -52,6 +52,28 @@ def test_wil_matches_oracle(oracle):
     assert np.abs(got - ref["del"]).max() <= TOL
 
 
+def test_wil_exact_division_pass_gives_the_same_bits(oracle, monkeypatch):
+    """The Hamming loop runs with the 3-instruction x/0.75 and only records whether an operand ever left its validity
+    window; if one did, that l is repeated with IEEE divisions.  PHSH_B200_WIL_EXACT=1 forces the repeat pass: identical
+    bits, since the fast quotient is the IEEE quotient inside the window."""
+    from phaseshifts_b200 import api, workloads
+    w = workloads.c5_wil(P=6, ne=64, nl=13)
+    fast = api.phsh_wil_batch(w["rs"], w["zs"], w["nrows"], w["Z"], w["RT"], w["e"], NL=13, NR=101)
+    monkeypatch.setenv("PHSH_B200_WIL_EXACT", "1")
+    exact = api.phsh_wil_batch(w["rs"], w["zs"], w["nrows"], w["Z"], w["RT"], w["e"], NL=13, NR=101)
+    assert np.array_equal(fast, exact)
+    ref = oracle.wil_batch(w["rs"], w["zs"], w["nrows"], w["Z"], w["RT"], w["e"], NL=13, NR=101)
+    assert np.abs(exact - ref["del"]).max() <= TOL
+    # a potential that vanishes (Z = 0, V = 0) makes Q start at exactly zero: operands of the division are 0 at l = 0,
+    # outside the window, so the repeat pass runs for real
+    monkeypatch.delenv("PHSH_B200_WIL_EXACT")
+    rs, zs = w["rs"][:1].copy(), np.zeros_like(w["zs"][:1])
+    z0 = api.phsh_wil_batch(rs, zs, w["nrows"][:1], np.array([0.0]), w["RT"][:1], w["e"], NL=5, NR=101)
+    r0 = oracle.wil_batch(rs, zs, w["nrows"][:1], np.array([0.0]), w["RT"][:1], w["e"], NL=5, NR=101)["del"]
+    both = np.isfinite(z0) & np.isfinite(r0)
+    assert np.array_equal(np.isfinite(z0), np.isfinite(r0)) and np.abs(z0[both] - r0[both]).max() <= TOL
+
+
 @pytest.mark.parametrize("NR,NL", [(201, 9), (101, 15), (57, 3)])
 def test_wil_grid_sizes(oracle, NR, NL):
     from phaseshifts_b200 import api, workloads
