@@ -195,6 +195,31 @@ def test_neighbour_shells_of_random_and_nearly_degenerate_cells(re_case):
         assert np.array_equal(out["shell_ad"][sl], ref["ad"]), s
 
 
+def test_many_atom_types_in_both_launch_configurations(re_case):
+    """20 atom types / 40 atoms in a large cell (154 KB of shared memory per CTA): alone (one 512-thread CTA) and as part of
+    a 150-structure batch (128-thread CTAs) -- same bits either way, and equal to the oracle."""
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    cl, _, rho0, nx0 = re_case
+    rng = np.random.default_rng(9)
+    nr = 20
+    pos = rng.uniform(0, 1, size=(40, 3))
+    c = dict(spa=14.0, rc=np.array([[1.0, 0.0, 0.0], [0.1, 1.0, 0.0], [0.0, 0.2, 1.1]]), nr=nr, nrr=np.full(nr, 2, dtype=np.int32),
+             z=np.full(nr, 75.0), zc=np.zeros(nr), rmt=rng.uniform(0.9, 1.3, size=nr), rk=pos, nform=2, alpha=0.7, nh=4)
+    rho, nx = rho0[:1], nx0[:1]
+    ref = cio.cavpot(c, np.repeat(rho, nr, axis=0), np.repeat(nx, nr), real32=False)
+    st = _struct(c, dens=np.zeros(nr, dtype=np.int32))
+    one = api.cavpot_batch([st], rho, nx, diagnostics=True)
+    _check(one, 0, ref, nr)
+    assert np.array_equal(one["shell_na"], ref["na"]) and list(one["stats"][0][:2]) == [ref["nint"], ref["npoint"]]
+    small = _struct(cl)
+    small["dens"] = np.zeros(2, dtype=np.int32)
+    many = api.cavpot_batch([small] * 75 + [st] + [small] * 74, rho, nx)
+    t0 = many["type_off"][75]
+    assert np.array_equal(many["pot"][t0:t0 + nr], one["pot"]) and many["mtz"][75] == one["mtz"][0]
+    assert np.array_equal(many["pot"][0:2], many["pot"][-2:])
+
+
 def test_structures_to_phase_shifts_on_the_device(re_case):
     """cavpot_batch(on_device) hands `pot`/`npts` straight to phsh_rel_batch (same grid, r*V, even stride): geometry
     variants -> muffin-tin potentials -> delta_l(E) without a host round trip; against the oracle chain to 1e-8 rad."""
