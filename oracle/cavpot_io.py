@@ -29,6 +29,10 @@ def _lib():
         L.orc_cavpot.argtypes = ([C.c_int, C.c_int, C.c_double, _dp, C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_int, C.c_double,
                                   C.c_int, C.c_int, C.c_double, _dp, _ip, _dp, _ip, _dp, _dp, _ip, _ip, _dp, _ip, _ip, _dp,
                                   _dp, _dp, _ip])
+        L.orc_hsin_density.restype = C.c_int
+        L.orc_hsin_density.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, _dp, C.c_int, C.c_int, _dp, _ip]
+        L.orc_clemin_density.restype = C.c_int
+        L.orc_clemin_density.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp, _ip]
         L._cavpot_ready = True
     return L
 
@@ -82,7 +86,7 @@ def read_cluster(path: str, real32: bool = True):
 
 
 def read_atomic(path: str, nr: int, real32: bool = True):
-    """The first ``nr`` blocks of atomic.i (unit 4).  Only 'RELA' blocks are restated here (phsh1.f:1136-1148)."""
+    """The first ``nr`` blocks of atomic.i (unit 4): 'RELA' (phsh1.f:1136-1148), 'HERM' (:588-607), 'CLEM' (:508-544)."""
     r = f32 if real32 else float
     with open(path, "r", errors="replace") as f:
         lines = f.read().split("\n")
@@ -91,20 +95,113 @@ def read_atomic(path: str, nr: int, real32: bool = True):
     for _ in range(nr):
         wfn = _pad(lines[pos], 4)[:4]
         pos += 1
-        if wfn != "RELA":
-            raise NotImplementedError("atomic.i block '%s': only RELA is handled by the oracle's file layer" % wfn)
-        name = _pad(lines[pos], 16)[:16]
-        iprint = iread(_pad(lines[pos + 1], 4)[0:4])
-        ln = _pad(lines[pos + 2], 40)
-        rmin = r(fread(ln[0:15], 8))
-        rmax = r(fread(ln[15:30], 8))
-        n = iread(ln[30:35])
-        zat = r(fread(ln[35:40], 2))
-        pos += 3
-        rs = np.array([r(fread(_pad(lines[pos + k], 15)[0:15], 10)) for k in range(n)])
-        pos += n
-        blocks.append(dict(kind="RELA", name=name, iprint=iprint, rmin=rmin, rmax=rmax, nr=n, z=zat, rs=rs))
+        if wfn == "RELA":
+            name = _pad(lines[pos], 16)[:16]
+            iprint = iread(_pad(lines[pos + 1], 4)[0:4])
+            ln = _pad(lines[pos + 2], 40)
+            rmin = r(fread(ln[0:15], 8))
+            rmax = r(fread(ln[15:30], 8))
+            n = iread(ln[30:35])
+            zat = r(fread(ln[35:40], 2))
+            pos += 3
+            rs = np.array([r(fread(_pad(lines[pos + k], 15)[0:15], 10)) for k in range(n)])
+            pos += n
+            blocks.append(dict(kind="RELA", name=name, iprint=iprint, rmin=rmin, rmax=rmax, nr=n, z=zat, rs=rs))
+        elif wfn == "HERM":
+            name = _pad(lines[pos], 16)[:16]
+            z = r(fread(_pad(lines[pos + 1], 9)[0:9], 4))
+            iprint = iread(_pad(lines[pos + 2], 4)[0:4])
+            nm = iread(_pad(lines[pos + 3], 4)[0:4])
+            nc = iread(_pad(lines[pos + 4], 4)[0:4])
+            pos += 5
+            lc, nn, frac, wf = [], [], [], []
+            for _ic in range(nc):
+                ln = _pad(lines[pos], 17)
+                lc.append(iread(ln[0:4]))
+                nn.append(iread(ln[4:8]))
+                frac.append(r(fread(ln[8:17], 4)))
+                pos += 1
+                vals = []
+                while len(vals) < nn[-1]:
+                    ln = _pad(lines[pos], 45)
+                    vals += [r(fread(ln[9 * k:9 * k + 9], 4)) for k in range(min(5, nn[-1] - len(vals)))]
+                    pos += 1
+                wf.append(vals)
+            blocks.append(dict(kind="HERM", name=name, z=z, iprint=iprint, nm=nm, lc=lc, n=nn, frac=frac, wf=wf))
+        elif wfn == "CLEM":
+            name = _pad(lines[pos], 16)[:16]
+            iprint = iread(_pad(lines[pos + 1], 4)[0:4])
+            nc = iread(_pad(lines[pos + 2], 4)[0:4])
+            pos += 3
+            bases, states = [], []
+            while True:
+                ns = iread(_pad(lines[pos], 4)[0:4])
+                pos += 1
+                if ns <= 0:
+                    break
+                nt, ex = [], []
+                for _k in range(ns):      # FORMAT(I4,F11.5) with format reversion: one pair per record
+                    ln = _pad(lines[pos], 15)
+                    nt.append(iread(ln[0:4]))
+                    ex.append(r(fread(ln[4:15], 5)))
+                    pos += 1
+                bases.append(dict(nt=nt, ex=ex))
+                while True:
+                    l = iread(_pad(lines[pos], 4)[0:4])
+                    pos += 1
+                    if l < 0:
+                        break
+                    fac = []
+                    while len(fac) < ns:
+                        ln = _pad(lines[pos], 55)
+                        fac += [r(fread(ln[11 * k:11 * k + 11], 5)) for k in range(min(5, ns - len(fac)))]
+                        pos += 1
+                    frac = r(fread(_pad(lines[pos], 11)[0:11], 5))
+                    pos += 1
+                    states.append(dict(basis=len(bases) - 1, lc=l, fac=fac, frac=frac))
+            blocks.append(dict(kind="CLEM", name=name, iprint=iprint, nc=nc, bases=bases, states=states))
+        else:
+            raise NotImplementedError("atomic.i block '%s': RELA, HERM and CLEM are handled by the oracle's file layer" % wfn)
     return blocks
+
+
+def density(block, real32: bool = True):
+    """(rho[250], NX) of one atomic.i block on the Loucks mesh."""
+    if block["kind"] == "RELA":
+        return rela_density(block, real32)
+    rho = np.zeros(NGRID)
+    nx = C.c_int(0)
+    if block["kind"] == "HERM":
+        nc = len(block["lc"])
+        stride = max(block["n"])
+        wf = np.zeros((nc, stride))
+        for ic, v in enumerate(block["wf"]):
+            wf[ic, :len(v)] = v
+        lc = np.array(block["lc"], dtype=np.int32)
+        nn = np.array(block["n"], dtype=np.int32)
+        frac = np.array(block["frac"], dtype=np.float64)
+        _lib().orc_hsin_density(int(real32), float(block["z"]), int(block["nm"]), nc, _i(lc), _i(nn), _d(frac), _d(wf), stride,
+                                int(block["iprint"]), _d(rho), C.byref(nx))
+        return rho, nx.value
+    bases, states = block["bases"], block["states"]
+    nb = len(bases)
+    stride = max(len(b["nt"]) for b in bases)
+    ns = np.array([len(b["nt"]) for b in bases], dtype=np.int32)
+    nt = np.zeros((nb, stride), dtype=np.int32)
+    ex = np.zeros((nb, stride))
+    for b, bb in enumerate(bases):
+        nt[b, :ns[b]] = bb["nt"]
+        ex[b, :ns[b]] = bb["ex"]
+    nc = len(states)
+    basis = np.array([s_["basis"] for s_ in states], dtype=np.int32)
+    lc = np.array([s_["lc"] for s_ in states], dtype=np.int32)
+    frac = np.array([s_["frac"] for s_ in states], dtype=np.float64)
+    fac = np.zeros((nc, stride))
+    for ic, s_ in enumerate(states):
+        fac[ic, :len(s_["fac"])] = s_["fac"]
+    _lib().orc_clemin_density(int(real32), nb, _i(ns), _i(nt), _d(ex), stride, nc, _i(basis), _i(lc), _d(fac), _d(frac), _d(rho),
+                              C.byref(nx))
+    return rho, nx.value
 
 
 def rela_density(block, real32: bool = True):
@@ -194,7 +291,7 @@ def cavpot_file(mtz_string: str, slab: int, atomic_file: str, cluster_file: str,
     rho = np.zeros((cl["nr"], NGRID))
     nx = np.zeros(cl["nr"], dtype=np.int32)
     for ir, b in enumerate(blocks):
-        rho[ir], nx[ir] = rela_density(b, real32)
+        rho[ir], nx[ir] = density(b, real32)
     esht = 0.0
     if slab == 1:
         esht = float(mtz_string.split()[0].replace("D", "E").replace("d", "e"))

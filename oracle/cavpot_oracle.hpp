@@ -18,7 +18,8 @@
 // (cluster_Re_bulk.i + atomic_Re.i -> mufftin_Re_bulk.d, NFORM=2, RELA densities,
 // MTZ sampling NH=10); tests/test_cavpot_oracle.py checks the restatement against
 // all 642 tabulated values.  The Madelung (MAD), MTZM, HERM/CLEM/POTE branches
-// have no fixture in the reference: PARITY UNPINNED for those branches.
+// have no fixture in the reference: PARITY UNPINNED for those branches (HSIN and
+// CLEMIN are additionally checked against analytic hydrogen / closed-shell densities).
 //
 // Precision model (same as phsh_oracle.hpp): Real=float is "as written" (REAL*4
 // with the DOUBLE PRECISION accumulators the Fortran declares), Real=double is
@@ -212,7 +213,7 @@ static inline Density<Real> clemin_density(const std::vector<ClemBasis<Real>>& b
         Real sum = Real(0);
         for (int ic = 0; ic < nc; ++ic) sum = sum + wc[ic] * wfc[ic][ix] * wfc[ic][ix];
         d.rho[ix] = sum;
-        if (sum < lit<Real>(1.0e-9f)) break;
+        if (static_cast<double>(sum) < 1.0e-9) break;  // IF(SUM.LT.1.0D-9): a DOUBLE PRECISION literal
     }
     d.nx = ix;  // Fortran: NX=IX at the GOTO, NGRID+1 when the loop runs out
     return d;

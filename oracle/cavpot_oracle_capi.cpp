@@ -18,6 +18,49 @@ int rela_impl(double rmin, double rmax, int nr, const double* rs, int iprint, do
 }
 
 template <class Real>
+int hsin_impl(double z, int nm, int nc, const int* lc, const int* n, const double* frac, const double* wf, int wf_stride,
+              int iprint, double* rho_out, int* nx_out) {
+    std::vector<Real> rx;
+    loucks_grid<Real>(rx);
+    std::vector<HsState<Real>> st(nc);
+    for (int ic = 0; ic < nc; ++ic) {
+        st[ic].lc = lc[ic];
+        st[ic].n = n[ic];
+        st[ic].frac = static_cast<Real>(frac[ic]);
+        st[ic].wf.assign(n[ic] + 1, Real(0));
+        for (int i = 1; i <= n[ic]; ++i) st[ic].wf[i] = static_cast<Real>(wf[static_cast<size_t>(ic) * wf_stride + i - 1]);
+    }
+    Density<Real> d = hsin_density<Real>(static_cast<Real>(z), nm, st, rx, iprint);
+    for (int i = 1; i <= NGRID; ++i) rho_out[i - 1] = static_cast<double>(d.rho[i]);
+    *nx_out = d.nx;
+    return 0;
+}
+
+template <class Real>
+int clemin_impl(int nbasis, const int* ns, const int* nt, const double* ex, int b_stride, int nc, const int* basis,
+                const int* lc, const double* fac, const double* frac, double* rho_out, int* nx_out) {
+    std::vector<Real> rx;
+    loucks_grid<Real>(rx);
+    std::vector<ClemBasis<Real>> bases(nbasis);
+    for (int b = 0; b < nbasis; ++b)
+        for (int k = 0; k < ns[b]; ++k) {
+            bases[b].nt.push_back(nt[b * b_stride + k]);
+            bases[b].ex.push_back(static_cast<Real>(ex[b * b_stride + k]));
+        }
+    std::vector<ClemState<Real>> st(nc);
+    for (int ic = 0; ic < nc; ++ic) {
+        st[ic].basis = basis[ic];
+        st[ic].lc = lc[ic];
+        st[ic].frac = static_cast<Real>(frac[ic]);
+        for (int k = 0; k < ns[basis[ic]]; ++k) st[ic].fac.push_back(static_cast<Real>(fac[ic * b_stride + k]));
+    }
+    Density<Real> d = clemin_density<Real>(bases, st, rx);
+    for (int i = 1; i <= NGRID; ++i) rho_out[i - 1] = static_cast<double>(d.rho[i]);
+    *nx_out = d.nx;
+    return 0;
+}
+
+template <class Real>
 int cavpot_impl(int asbuilt, double spa, const double* rc_in, int nr, const int* nrr, const double* z, const double* zc,
                 const double* rmt, const double* rk_in, int nform, double alpha, int nh, int slab, double esht,
                 const double* rho, const int* nx, double* mtz_out, int* npts, double* out_r, double* out_v, int* jrmt,
@@ -96,6 +139,20 @@ extern "C" {
 int orc_rela_density(int real32, double rmin, double rmax, int nr, const double* rs, int iprint, double* rho_out, int* nx_out) {
     return real32 ? rela_impl<float>(rmin, rmax, nr, rs, iprint, rho_out, nx_out)
                   : rela_impl<double>(rmin, rmax, nr, rs, iprint, rho_out, nx_out);
+}
+
+// HSIN (phsh1.f:572-635): Herman-Skillman orbitals wf[ic][0..n[ic]) on the H-S mesh -> density on the Loucks mesh.
+int orc_hsin_density(int real32, double z, int nm, int nc, const int* lc, const int* n, const double* frac, const double* wf,
+                     int wf_stride, int iprint, double* rho_out, int* nx_out) {
+    return real32 ? hsin_impl<float>(z, nm, nc, lc, n, frac, wf, wf_stride, iprint, rho_out, nx_out)
+                  : hsin_impl<double>(z, nm, nc, lc, n, frac, wf, wf_stride, iprint, rho_out, nx_out);
+}
+
+// CLEMIN (phsh1.f:493-570): Clementi orbitals; basis b has ns[b] (nt, ex) pairs, state ic uses basis[ic] with fac[ic][..].
+int orc_clemin_density(int real32, int nbasis, const int* ns, const int* nt, const double* ex, int b_stride, int nc,
+                       const int* basis, const int* lc, const double* fac, const double* frac, double* rho_out, int* nx_out) {
+    return real32 ? clemin_impl<float>(nbasis, ns, nt, ex, b_stride, nc, basis, lc, fac, frac, rho_out, nx_out)
+                  : clemin_impl<double>(nbasis, ns, nt, ex, b_stride, nc, basis, lc, fac, frac, rho_out, nx_out);
 }
 
 // CAVPOT from the densities on (phsh1.f:188-426).  rc_in[3*(j-1)+i-1] = RC(I,J) and rk_in[3*(a-1)+i-1] = RK(I,a) in units of

@@ -86,6 +86,10 @@ _SIGNATURES = {
     "phsh_b200_cavpot_batch_device": (C.c_int, [C.POINTER(CavpotBatch), C.POINTER(CavpotResult), C.c_int, C.c_void_p]),
     "phsh_b200_cavpot_rela_density": (C.c_int, [C.c_double, C.c_double, C.c_int, _dp, C.c_int, _dp, C.POINTER(C.c_int),
                                                 C.c_int]),
+    "phsh_b200_cavpot_hsin_density": (C.c_int, [C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, _dp,
+                                                C.POINTER(C.c_int), C.c_int]),
+    "phsh_b200_cavpot_clemin_density": (C.c_int, [C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp,
+                                                  C.POINTER(C.c_int), C.c_int]),
     "phsh_b200_cavpot_file": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
                                         C.POINTER(FileOpts), C.POINTER(C.c_double)]),
     "phsh_b200_selftest_cavpot": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),

@@ -317,6 +317,47 @@ def cavpot_rela_density(rmin, rmax, rs, iprint=0, device=0):
     return rho, int(nx.value)
 
 
+def cavpot_hsin_density(z, nm, lc, n, frac, wf, iprint=0, device=0):
+    """``HSIN`` (``libphsh.f:2712-2807``): Herman-Skillman orbitals ``wf[ic][:n[ic]]`` (r*R(r) on the H-S mesh of atomic number
+    ``z`` whose interval doubles every ``nm`` points) -> (rho[250] on Loucks' mesh, NX)."""
+    lc = np.ascontiguousarray(lc, dtype=np.int32).reshape(-1)
+    n = np.ascontiguousarray(n, dtype=np.int32).reshape(-1)
+    frac = _np64(frac).reshape(-1)
+    stride = int(n.max())
+    w = np.zeros((lc.size, stride))
+    for ic in range(lc.size):
+        w[ic, :n[ic]] = np.asarray(wf[ic], dtype=np.float64)[:n[ic]]
+    rho = np.zeros(250)
+    nx = C.c_int(0)
+    _lib.check(_lib.load().phsh_b200_cavpot_hsin_density(float(z), int(nm), int(lc.size), _ptr(lc), _ptr(n), _ptr(frac), _ptr(w),
+                                                        stride, int(iprint), _ptr(rho), C.byref(nx), int(device)))
+    return rho, int(nx.value)
+
+
+def cavpot_clemin_density(bases, states, device=0):
+    """``CLEMIN`` (``libphsh.f:2602-2710``): ``bases`` = [dict(nt=[..], ex=[..])], ``states`` = [dict(basis=i, lc=l, fac=[..],
+    frac=f)] -> (rho[250] on Loucks' mesh, NX)."""
+    nb, nc = len(bases), len(states)
+    stride = max(len(b["nt"]) for b in bases)
+    ns = np.array([len(b["nt"]) for b in bases], dtype=np.int32)
+    nt = np.zeros((nb, stride), dtype=np.int32)
+    ex = np.zeros((nb, stride))
+    for i, b in enumerate(bases):
+        nt[i, :ns[i]] = b["nt"]
+        ex[i, :ns[i]] = b["ex"]
+    basis = np.array([s["basis"] for s in states], dtype=np.int32)
+    lc = np.array([s["lc"] for s in states], dtype=np.int32)
+    frac = np.array([s["frac"] for s in states], dtype=np.float64)
+    fac = np.zeros((nc, stride))
+    for i, s in enumerate(states):
+        fac[i, :len(s["fac"])] = s["fac"]
+    rho = np.zeros(250)
+    nx = C.c_int(0)
+    _lib.check(_lib.load().phsh_b200_cavpot_clemin_density(nb, _ptr(ns), _ptr(nt), _ptr(ex), stride, nc, _ptr(basis), _ptr(lc),
+                                                          _ptr(fac), _ptr(frac), _ptr(rho), C.byref(nx), int(device)))
+    return rho, int(nx.value)
+
+
 def cavpot_pack(structures):
     """Flatten a sequence of structure dicts (see ``cavpot_batch``) into the ragged arrays of ``phsh_b200_cavpot_batch``.
     Lengths are multiplied by the lattice constant here, as ``CAVPOT`` does on input (``libphsh.f:2133-2137, 2209-2211``)."""

@@ -195,6 +195,49 @@ def test_neighbour_shells_of_random_and_nearly_degenerate_cells(re_case):
         assert np.array_equal(out["shell_ad"][sl], ref["ad"]), s
 
 
+def test_herman_skillman_and_clementi_densities_and_mixed_atomic_file(tmp_path):
+    """The two other charge-density forms of atomic.i: HSIN (table -> CHGRID on the GPU, bit-identical to the oracle) and
+    CLEMIN (Slater orbitals evaluated on the GPU: device exp vs libm, 1e-13 relative); then a cluster whose three atom types
+    take their densities from a RELA, a CLEM and a HERM block of one atomic file, through the file interface."""
+    from cavpot_inputs import hydrogen_clem, hydrogen_herm, neon_like_clem
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    rela = open(os.path.join(RE, "atomic_Re.i")).read().split("\n")[:1004]
+    (tmp_path / "a.i").write_text("\n".join(rela + neon_like_clem() + hydrogen_herm()) + "\n")
+    blocks = cio.read_atomic(str(tmp_path / "a.i"), 3, real32=False)
+    assert [b["kind"] for b in blocks] == ["RELA", "CLEM", "HERM"]
+    o_c, n_c = cio.density(blocks[1], real32=False)
+    g_c, gn_c = api.cavpot_clemin_density(blocks[1]["bases"], blocks[1]["states"])
+    assert gn_c == n_c and np.abs(g_c - o_c).max() <= 1e-12 * o_c.max() and (g_c[n_c:] == 0).all()
+    b = blocks[2]
+    o_h, n_h = cio.density(b, real32=False)
+    g_h, gn_h = api.cavpot_hsin_density(b["z"], b["nm"], b["lc"], b["n"], b["frac"], b["wf"], b["iprint"])
+    assert gn_h == n_h and np.array_equal(g_h, o_h)
+    (tmp_path / "c.i").write_text("\n".join([
+        "mixed densities", "  7.0000", "  1.0000  0.0000  0.0000", "  0.0000  1.0000  0.0000", "  0.0000  0.0000  1.0000", "   3",
+        "HEAVY", "   1 75.0000  0.0000  2.2000", "  0.0000  0.0000  0.0000",
+        "TEN ELECTRONS", "   1 10.0000  0.0000  1.4000", "  0.5000  0.5000  0.0000",
+        "ONE ELECTRON", "   1  1.0000  0.0000  0.9000", "  0.5000  0.0000  0.5000",
+        "   0", "  0.7000", "   6"]) + "\n")
+    g = [str(tmp_path / n) for n in ("g.d", "g.i", "g.txt")]
+    o = [str(tmp_path / n) for n in ("o.d", "o.i", "o.txt")]
+    mtz = api.cavpot_file("", 0, str(tmp_path / "a.i"), str(tmp_path / "c.i"), *g)
+    omtz, res, _ = cio.cavpot_file("", 0, str(tmp_path / "a.i"), str(tmp_path / "c.i"), *o, real32=False)
+    assert abs(mtz - omtz) < 1e-6
+    la, lb = open(g[0]).read().split("\n"), open(o[0]).read().split("\n")
+    assert len(la) == len(lb) and la[0] == "   3"
+    bad = [i for i, (x, y) in enumerate(zip(la, lb)) if x != y]
+    for i in bad:    # 5 printed digits: at most a last-digit flip
+        xv, yv = np.array(la[i].split(), dtype=float), np.array(lb[i].split(), dtype=float)
+        assert np.abs(xv - yv).max() <= 1.0001e-4 * np.abs(yv).max()
+    assert len(bad) <= 3
+    # 'POTE' is refused with the reason
+    (tmp_path / "p.i").write_text("POTE\n   3\n")
+    with pytest.raises(api._lib.PhshB200Error) as e:
+        api.cavpot_file("", 0, str(tmp_path / "p.i"), str(tmp_path / "c.i"), *g)
+    assert "POTE" in str(e.value)
+
+
 def test_many_atom_types_in_both_launch_configurations(re_case):
     """20 atom types / 40 atoms in a large cell (154 KB of shared memory per CTA): alone (one 512-thread CTA) and as part of
     a 150-structure batch (128-thread CTAs) -- same bits either way, and equal to the oracle."""
@@ -359,7 +402,7 @@ def test_error_behaviour(tmp_path):
         api.cavpot_file("", 0, ok_a, str(trunc), *outs)
     assert e.value.code == -1
     herm = tmp_path / "herm.i"
-    herm.write_text("HERM\n" + "".join(open(ok_a).readlines()[1:]))
+    herm.write_text("XXXX\n" + "".join(open(ok_a).readlines()[1:]))
     with pytest.raises(PhshB200Error) as e:
         api.cavpot_file("", 0, str(herm), ok_c, *outs)
     assert e.value.code == -1 and "RELA" in str(e.value)

@@ -145,3 +145,24 @@ def test_oracle_runs_on_the_reference_example_inputs(stem):
         v = r["v"][i, :r["npts"][i]]
         assert np.isfinite(v).all() and (v[:5] < 0).all()
         assert abs(v[0] / (-2.0 * cl["z"][i])) - 1.0 < 1e-2      # r*V -> -2Z at the origin
+
+
+def test_herman_skillman_and_clementi_forms(tmp_path):
+    """HSIN / CLEMIN have no fixture in the reference (PARITY UNPINNED for these two input forms); physics instead: a
+    hydrogen 1s orbital given either way yields 4 r^2 exp(-2r) on Loucks' mesh, integrating to its occupation, and a
+    closed-shell ten-electron atom integrates to ten."""
+    from cavpot_inputs import hydrogen_clem, hydrogen_herm, neon_like_clem
+    x = np.exp(np.float64(np.float32(-8.8)) + np.float64(np.float32(0.05)) * np.arange(250))
+    (tmp_path / "a.i").write_text("\n".join(hydrogen_clem() + hydrogen_herm() + neon_like_clem()) + "\n")
+    blocks = cio.read_atomic(str(tmp_path / "a.i"), 3, real32=False)
+    assert [b["kind"] for b in blocks] == ["CLEM", "HERM", "CLEM"]
+    rho_c, nx_c = cio.density(blocks[0], real32=False)
+    rho_h, nx_h = cio.density(blocks[1], real32=False)
+    exact = 4.0 * x * x * np.exp(-2.0 * x)
+    assert 200 < nx_c <= 250 and np.abs(rho_c[:nx_c] - exact[:nx_c]).max() < 1e-9
+    assert nx_h < 250 and np.abs(rho_h[:nx_h] - exact[:nx_h]).max() < 2e-4      # F9.4 table, 3-point interpolation
+    assert abs(np.trapezoid(rho_c[:nx_c], x[:nx_c]) - 1.0) < 1e-3
+    rho_n, nx_n = cio.density(blocks[2], real32=False)
+    assert abs(np.trapezoid(rho_n[:nx_n], x[:nx_n]) - 10.0) < 0.05
+    r32, n32 = cio.density(blocks[2], real32=True)
+    assert n32 == nx_n and np.abs(r32 - rho_n).max() < 1e-4 * rho_n.max()

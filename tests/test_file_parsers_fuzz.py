@@ -142,6 +142,17 @@ def test_cavpot_file_mutations(tmp_path, seed, mode, which):
     _call(api.cavpot_file, "-1.5", 1, str(a), str(c), str(tmp_path / "m.d"), str(tmp_path / "o.i"), "")
 
 
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(seed=st.integers(0, 10 ** 9), mode=st.integers(0, 3))
+def test_cavpot_file_herm_clem_mutations(tmp_path, seed, mode):
+    """The Herman-Skillman and Clementi block readers (group / state loops terminated by sentinels) on mutated input."""
+    from cavpot_inputs import hydrogen_herm, neon_like_clem
+    from phaseshifts_b200 import api
+    a = tmp_path / "a.i"
+    a.write_text(_mutate("\n".join(neon_like_clem() + hydrogen_herm()) + "\n", seed, mode))
+    _call(api.cavpot_file, "", 0, str(a), CLU, str(tmp_path / "m.d"), str(tmp_path / "o.i"), "")
+
+
 @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(body=_text)
 def test_cavpot_file_on_garbage(tmp_path, body):
