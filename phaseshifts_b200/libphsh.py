@@ -15,8 +15,8 @@ The producer of the path's input is here too:
     cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file) -> float
                                                  libphsh.f:2070  (called from model.py:935)
 
-The atomic step (``hartfock``, ``hb``) is NOT part of this package: if the real extension is importable it is
-delegated to it, otherwise it raises.
+The atomic step (``hartfock``) is NOT part of this package: if the real extension is importable it is delegated to
+it, otherwise it raises.  ``hb`` (a closed-form helper the f2py module also exports) is evaluated directly.
 
 Environment switches (read at call time):
   PHSH_B200_DEVICE=<n>        CUDA device index (default 0)
@@ -101,4 +101,11 @@ def cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, outpu
 
 
 hartfock = _upstream("hartfock")  # libphsh.f:60    atomic charge densities (step 0)
-hb = _upstream("hb")              # libphsh.f:1443  helper of hartfock
+
+
+def hb(x, factor):
+    """The cut-off function of the pseudopotential generator (``libphsh.f:1443-1452``), exported by the f2py module:
+    ``0.01**((sinh(x/factor)/1.1752)**2)`` for ``x <= 3``, else 0.  A closed form, evaluated here."""
+    import math
+    x, factor = float(x), float(factor)
+    return 0.0 if x > 3.0 else 0.01 ** ((math.sinh(x / factor) / 1.1752) ** 2.0)

@@ -126,9 +126,9 @@ def test_standin_module_surface(monkeypatch):
     for fn in ("phsh_rel", "phsh_cav", "phsh_wil"):
         assert len(inspect.signature(getattr(libphsh, fn)).parameters) == 4
     assert len(inspect.signature(libphsh.cavpot).parameters) == 7   # libphsh.f:2070-2071
-    for fn in ("hartfock", "hb"):
-        with pytest.raises(NotImplementedError):
-            getattr(libphsh, fn)(1, 2)
+    with pytest.raises(NotImplementedError):
+        libphsh.hartfock("atorb_Re")
+    assert libphsh.hb(4.0, 1.0) == 0.0 and abs(libphsh.hb(1.0, 1.0) - 0.01) < 3e-7 and libphsh.hb(0.0, 2.0) == 1.0
     seen = {}
     monkeypatch.setattr(api, "cavpot_file", lambda *a, **k: seen.update(cav=a, cavkw=k) or -1.5)
     assert libphsh.cavpot(b" -1.0 ", 1, "a.i ", "c.i", "m.d", "o.i", "info.txt") == -1.5
