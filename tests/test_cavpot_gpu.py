@@ -238,6 +238,26 @@ def test_herman_skillman_and_clementi_densities_and_mixed_atomic_file(tmp_path):
     assert "POTE" in str(e.value)
 
 
+def test_fine_sampling_grid_spans_many_passes(re_case):
+    """NH = 24 -> 13824 sample points, ~3900 interstitial: the ordered compaction list is filled and drained dozens of times
+    (128-thread CTAs in a 150-structure batch, 512-thread CTA alone); VHAR/VEX must stay bit-identical to the serial sum."""
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    cl, _, rho, nx = re_case
+    c = dict(cl)
+    c["nh"] = 24
+    ref = cio.cavpot(c, rho, nx, real32=False)
+    assert ref["npoint"] == 13824 and ref["nint"] > 3000
+    one = api.cavpot_batch([_struct(c)], rho, nx, diagnostics=True)
+    assert one["vhar"][0] == ref["vhar"] and one["vex"][0] == ref["vex"]
+    assert list(one["stats"][0][:2]) == [ref["nint"], ref["npoint"]]
+    c2 = dict(cl)
+    c2["nh"] = 2
+    many = api.cavpot_batch([_struct(c2)] * 100 + [_struct(c)] + [_struct(c2)] * 49, rho, nx)
+    assert many["vhar"][100] == ref["vhar"] and many["vex"][100] == ref["vex"]
+    _check(many, 200, ref, 2)
+
+
 def test_many_atom_types_in_both_launch_configurations(re_case):
     """20 atom types / 40 atoms in a large cell (154 KB of shared memory per CTA): alone (one 512-thread CTA) and as part of
     a 150-structure batch (128-thread CTAs) -- same bits either way, and equal to the oracle."""
