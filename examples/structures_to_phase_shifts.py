@@ -25,13 +25,14 @@ def main():
     rho, nx = api.cavpot_rela_density(b["rmin"], b["rmax"], b["rs"], b["iprint"])   # atomic_Re.i -> Loucks' mesh
     batch = api.cavpot_pack(w["structures"])
     grid = api.rel_energy_grid(20.0, 2.0, 400.0)                                      # 191 energies
-    for rep in range(2):
+    for rep in range(4):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        pots = api.cavpot_batch(batch, rho[None, :], [nx], on_device=True)            # pot [2S][422], npts [2S] in HBM
-        delta = api.phsh_rel_batch(pots["pot"], pots["npts"], grid["e_l"], 10, energies_l0=grid["e_l0"], unwrap=True)
+        delta, pots = api.structures_to_phase_shifts(batch, rho[None, :], [nx], grid["e_l"], 10,
+                                                     energies_l0=grid["e_l0"])          # pot [2S][422] stays in HBM
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        print("pass %d: %.1f ms" % (rep, dt * 1e3))
     print("%d structures (%d atom types) -> %s phase shifts in %.1f ms; muffin-tin zeros %.4f .. %.4f Ryd"
           % (S, delta.shape[0], "x".join(map(str, delta.shape)), dt * 1e3, float(pots["mtz"].min()), float(pots["mtz"].max())))
     d = delta.cpu().numpy()

@@ -476,6 +476,19 @@ def _cavpot_batch_device(keep, S, T, A, n_dens, device):
                 _inputs=d)
 
 
+def structures_to_phase_shifts(structures, rho, nx, energies_ryd, lmax, *, energies_l0=None, unwrap=True, device=0, **rel_kwargs):
+    """cluster geometries -> muffin-tin potentials (``cavpot``, NFORM=2) -> relativistic phase shifts, without leaving
+    the GPU: ``cavpot_batch(on_device=True)`` leaves r*V(r) on ``phsh_rel``'s own radial grid in HBM and ``phsh_rel_batch``
+    integrates those tables.  Returns ``(delta [T, NE, lmax+1] CUDA tensor, potentials dict)``; row t belongs to atom type
+    ``t - type_off[s]`` of structure ``s``."""
+    pk = structures if isinstance(structures, dict) else cavpot_pack(structures)
+    if np.any(np.asarray(pk["nform"]) != 2):
+        raise ValueError("phsh_rel reads NFORM=2 potentials: every structure needs nform=2")
+    pots = cavpot_batch(pk, rho, nx, device=device, on_device=True)
+    delta = phsh_rel_batch(pots["pot"], pots["npts"], energies_ryd, lmax, energies_l0=energies_l0, unwrap=unwrap, **rel_kwargs)
+    return delta, pots
+
+
 def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file, *, device=0):
     """``libphsh.cavpot`` with its seven arguments (``libphsh.f:2070-2071``); returns the muffin-tin zero of a bulk run."""
     opts = _lib.FileOpts(0, 0, 0, int(device))

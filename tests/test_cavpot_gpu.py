@@ -297,7 +297,10 @@ def test_structures_to_phase_shifts_on_the_device(re_case):
         c["rmt"] = np.round(cl["rmt"] * (1 + 0.08 * rng.uniform(-1, 1)), 4)
         c["rk"] = cl["rk"] + np.round(0.01 * rng.normal(size=cl["rk"].shape), 4)
         cls.append(c)
+    d2, p2 = api.structures_to_phase_shifts([_struct(c) for c in cls], rho, nx, api.rel_energy_grid(20.0, 5.0, 300.0)["e_l"], 12,
+                                            energies_l0=api.rel_energy_grid(20.0, 5.0, 300.0)["e_l0"])
     dev = api.cavpot_batch([_struct(c) for c in cls], rho, nx, on_device=True)
+    assert torch.equal(p2["pot"], dev["pot"])
     host = api.cavpot_batch([_struct(c) for c in cls], rho, nx)
     assert dev["pot"].is_cuda and dev["pot"].shape == (12, 422)
     assert np.array_equal(dev["pot"].cpu().numpy()[:, :421], host["pot"]) and np.array_equal(dev["npts"].cpu().numpy(), host["npts"])
@@ -305,6 +308,7 @@ def test_structures_to_phase_shifts_on_the_device(re_case):
     g = api.rel_energy_grid(20.0, 5.0, 300.0)
     delta = api.phsh_rel_batch(dev["pot"], dev["npts"], g["e_l"], 12, energies_l0=g["e_l0"], unwrap=True)
     torch.cuda.synchronize()
+    assert torch.equal(d2, delta)
     delta = delta.cpu().numpy()
     assert delta.shape == (12, 57, 13) and np.isfinite(delta).all()
     for s, c in enumerate(cls):
