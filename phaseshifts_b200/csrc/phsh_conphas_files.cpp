@@ -9,6 +9,7 @@
 // including the quirks of the Python (energies taken from the first input file, extra rows appended to the
 // first n_phases rows, the header's N capped at 250).
 #include <cctype>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -72,9 +73,17 @@ std::vector<std::string> split_ws(const std::string& s) {
 }
 
 bool to_double(const std::string& s, double* v) {
+    // plain decimal tokens (the whole phasout) go through from_chars; anything else (leading '+', hex, inf/nan spellings,
+    // out-of-range) keeps strtod's behaviour
+    const char* b = s.c_str();
+    const char* e = b + s.size();
+    if (!s.empty() && s[0] != '+') {
+        const auto r = std::from_chars(b, e, *v);
+        if (r.ec == std::errc() && r.ptr == e) return true;
+    }
     char* end = nullptr;
-    *v = strtod(s.c_str(), &end);
-    return end != s.c_str() && *end == '\0';
+    *v = strtod(b, &end);
+    return end != b && *end == '\0';
 }
 
 std::string basename_of(const std::string& p) {
@@ -100,6 +109,21 @@ std::string fmt(const char* f, double v) {
     char b[64];
     snprintf(b, sizeof b, f, v);
     return b;
+}
+
+// "%W.Pf" through std::to_chars (prints what printf prints -- the correctly rounded decimal -- several times faster)
+inline void put_fixed(std::string* out, double v, int width, int prec) {
+    char b[400];
+    const auto r = std::to_chars(b, b + sizeof b - 1, v, std::chars_format::fixed, prec);
+    int n;
+    if (r.ec != std::errc()) {
+        n = snprintf(b, sizeof b, "%*.*f", width, prec, v);
+        out->append(b, n);
+        return;
+    }
+    n = static_cast<int>(r.ptr - b);
+    if (n < width) out->append(width - n, ' ');
+    out->append(b, n);
 }
 
 struct Section {
@@ -262,10 +286,22 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
             set_error("cannot write '%s'", dataph.c_str());
             return PHSH_B200_EIO;
         }
-        for (int kk = 0; kk <= lmax; ++kk) {
-            fprintf(f, "\"L = %d\n", kk);
-            for (int ii = 0; ii < n_phases; ++ii) fprintf(f, "%9.7f\t%9.7f\n", energy[ii] / HARTREE, conpha[i][ii][kk]);
-            fputs("\n", f);
+        {
+            std::string txt;
+            txt.reserve(static_cast<size_t>(lmax + 1) * (n_phases + 2) * 24);
+            std::vector<std::string> ecol(n_phases);
+            for (int ii = 0; ii < n_phases; ++ii) put_fixed(&ecol[ii], energy[ii] / HARTREE, 9, 7);
+            for (int kk = 0; kk <= lmax; ++kk) {
+                txt += "\"L = " + std::to_string(kk) + "\n";
+                for (int ii = 0; ii < n_phases; ++ii) {
+                    txt += ecol[ii];
+                    txt.push_back('\t');
+                    put_fixed(&txt, conpha[i][ii][kk], 9, 7);
+                    txt.push_back('\n');
+                }
+                txt.push_back('\n');
+            }
+            fwrite(txt.data(), 1, txt.size(), f);
         }
         fclose(f);
     }
@@ -302,13 +338,18 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
         }
         fprintf(f, "%d %8.2f %8.2f %8.2f %8.2f phaseshifts %s\n", n_inputs, c[0], c[1], c[2], c[3], ts.c_str());
         for (int ie = 0; ie < n_phases; ++ie) {
-            fprintf(f, "%7.4f\n", energy[ie] / HARTREE);
+            {
+                std::string erow;
+                put_fixed(&erow, energy[ie] / HARTREE, 7, 4);
+                erow.push_back('\n');
+                fwrite(erow.data(), 1, erow.size(), f);
+            }
             for (int ii = 0; ii < n_inputs; ++ii)
                 for (int l0 = 0; l0 <= lmax; l0 += 10) {
                     std::string row;
                     for (int l = l0; l <= lmax && l < l0 + 10; ++l) {
                         if (l > l0) row += " ";
-                        row += fmt("%7.4f", conpha[ii][ie][l]);
+                        put_fixed(&row, conpha[ii][ie][l], 7, 4);
                     }
                     while (!row.empty() && isspace(static_cast<unsigned char>(row.back()))) row.pop_back();
                     fprintf(f, "%s\n", row.c_str());
@@ -319,10 +360,16 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
         for (int l = 0; l <= lmax; ++l) fprintf(f, "l=%d ", l);
         fputs("\n", f);
         for (int ie = 0; ie < n_phases; ++ie) {
-            fprintf(f, "%7.4f ", energy[ie] / HARTREE);
+            std::string row;
+            put_fixed(&row, energy[ie] / HARTREE, 7, 4);
+            row.push_back(' ');
             for (int ii = 0; ii < n_inputs; ++ii)
-                for (int l = 0; l <= lmax; ++l) fprintf(f, "%7.4f ", conpha[ii][ie][l]);
-            fputs("\n", f);
+                for (int l = 0; l <= lmax; ++l) {
+                    put_fixed(&row, conpha[ii][ie][l], 7, 4);
+                    row.push_back(' ');
+                }
+            row.push_back('\n');
+            fwrite(row.data(), 1, row.size(), f);
         }
     } else {
         if (fmtname == "cleed") {
@@ -348,12 +395,16 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
             }
             fprintf(f, "%d %d neng lmax (calculated by %s on %s)\n", neng, lmax, user.c_str(), ts.c_str());
         }
+        std::string txt;
+        txt.reserve(static_cast<size_t>(n_phases) * (8 + 7 * (lmax + 2) * std::max(n_inputs, 1)));
         for (int ie = 0; ie < n_phases; ++ie) {
-            fprintf(f, "%7.4f\n", energy[ie] / HARTREE);
+            put_fixed(&txt, energy[ie] / HARTREE, 7, 4);
+            txt.push_back('\n');
             for (int ii = 0; ii < n_inputs; ++ii)
-                for (int l = 0; l <= lmax; ++l) fprintf(f, "%7.4f", conpha[ii][ie][l]);
-            fputs("\n", f);
+                for (int l = 0; l <= lmax; ++l) put_fixed(&txt, conpha[ii][ie][l], 7, 4);
+            txt.push_back('\n');
         }
+        fwrite(txt.data(), 1, txt.size(), f);
     }
     fclose(f);
     return 0;
