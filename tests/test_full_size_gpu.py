@@ -134,3 +134,60 @@ def test_edge_cases():
     jri = np.array([7, 100, 326], dtype=np.int32)
     d = api.phsh_rel_batch(w["pot"], jri, w["grid"]["e_l"], 2)
     assert d.shape == (3, 33, 3) and np.isfinite(d).all()
+
+
+def test_c6_cavpot_full_batch_properties():
+    """The producer workload at full size (4096 perturbed Re(0001) cells, one launch) through properties that need no
+    oracle run: determinism, independence of the position in the batch and of the batch size (128-thread CTAs vs the
+    512-thread CTA a lone structure gets), invariance under relabelling the two atom types, the analytic effect of a slab
+    shift, and r*V -> -2Z at the origin; plus oracle parity on a sample.  (Moving an atom by a lattice vector is NOT an
+    invariance of this algorithm: MTZ tests the spheres of the home cell and its 7 upper neighbours only, phsh1.f:840-858,
+    so atoms are expected inside the home cell -- that case is checked against the oracle instead.)"""
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api, workloads
+    w = workloads.c6_cavpot()
+    b = w["rela"]
+    rho0, nx0 = api.cavpot_rela_density(b["rmin"], b["rmax"], b["rs"], b["iprint"])
+    rho, nx = rho0[None, :], np.array([nx0], dtype=np.int32)
+    S = len(w["structures"])
+    pk = api.cavpot_pack(w["structures"])
+    out = api.cavpot_batch(pk, rho, nx)
+    again = api.cavpot_batch(pk, rho, nx)
+    assert out["pot"].shape == (2 * S, 421) and np.array_equal(out["pot"], again["pot"]) and np.array_equal(out["mtz"], again["mtz"])
+    assert np.isfinite(out["pot"]).all() and (out["npts"] >= 300).all() and (out["npts"] <= 340).all()
+    assert np.all(out["mtz"] < -1.4) and np.all(out["mtz"] > -1.9)
+    assert np.abs(out["pot"][:, 0] / -150.0 - 1.0).max() < 2e-3                      # r*V(r -> 0) = -2Z, Z = 75
+    # position in the batch / batch size / CTA width do not matter
+    idx = [0, 1, 777, 2048, 4095]
+    sub = api.cavpot_batch([w["structures"][i] for i in idx], rho, nx)
+    for k, i in enumerate(idx):
+        assert np.array_equal(sub["pot"][2 * k:2 * k + 2], out["pot"][2 * i:2 * i + 2]) and sub["mtz"][k] == out["mtz"][i]
+    # relabelling the two atom types permutes the rows.  The neighbour scan and the MTZ sums run in another order, so not
+    # bit for bit: 1e-9 on values up to 150
+    st = dict(w["structures"][5])
+    sw = dict(st, rk=np.asarray(st["rk"])[::-1].copy())
+    # an atom moved by a lattice vector: the same crystal
+    mv = dict(st, rk=np.asarray(st["rk"]) + np.array([[0.0, 0.0, 0.0], np.asarray(st["rc"])[0]]))
+    r = api.cavpot_batch([st, sw, mv], rho, nx)
+    n = int(r["npts"][0])
+    assert np.abs(r["pot"][2, :n] - r["pot"][1, :n]).max() < 1e-9 and np.abs(r["pot"][3, :n] - r["pot"][0, :n]).max() < 1e-9
+    assert abs(r["mtz"][1] - r["mtz"][0]) < 1e-11
+    cm = dict(spa=mv["spa"], rc=mv["rc"], nr=2, nrr=np.array(mv["nrr"], dtype=np.int32), z=np.array(mv["z"]), zc=np.array(mv["zc"]),
+              rmt=np.array(mv["rmt"]), rk=mv["rk"], nform=2, alpha=mv["alpha"], nh=mv["nh"])
+    refm = cio.cavpot(cm, np.stack([rho0, rho0]), np.array([nx0, nx0], dtype=np.int32), real32=False)
+    assert abs(refm["mtz"] - r["mtz"][0]) > 1e-3                                       # the reference algorithm's own behaviour
+    assert np.abs(r["pot"][4:6, :n] - refm["v"][:, :n]).max() <= 1e-11 * 150.0 and r["vhar"][2] == refm["vhar"]
+    # slab run with the own muffin-tin zero + d: V shifted by -d, i.e. r*V by -d*r on the Waber grid
+    sl = api.cavpot_batch([dict(st, slab=1, esht=float(r["mtz"][0]) + 0.125)], rho, nx)
+    rgrid = 60.0 * np.exp(0.03125 * (np.arange(1, n + 1) - 421))
+    assert np.abs((sl["pot"][0, :n] - r["pot"][0, :n]) + 0.125 * rgrid).max() < 1e-6
+    # oracle parity on a sample
+    for i in (3, 1500, 4000):
+        s_ = w["structures"][i]
+        c = dict(spa=s_["spa"], rc=s_["rc"], nr=2, nrr=np.array(s_["nrr"], dtype=np.int32), z=np.array(s_["z"]),
+                 zc=np.array(s_["zc"]), rmt=np.array(s_["rmt"]), rk=s_["rk"], nform=2, alpha=s_["alpha"], nh=s_["nh"])
+        ref = cio.cavpot(c, np.stack([rho0, rho0]), np.array([nx0, nx0], dtype=np.int32), real32=False)
+        k = int(ref["npts"][0])
+        assert list(out["npts"][2 * i:2 * i + 2]) == list(ref["npts"])
+        assert np.abs(out["pot"][2 * i:2 * i + 2, :k] - ref["v"][:, :k]).max() <= 1e-11 * 150.0
+        assert out["vhar"][i] == ref["vhar"] and out["vex"][i] == ref["vex"]
