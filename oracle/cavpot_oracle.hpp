@@ -12,7 +12,9 @@
 //   phaseshifts/lib/libphsh.f           the as-built copies (:2070-3578).  They are
 //       the same arithmetic except NBR (:3293-3398), whose GOTO->exit rewrite leaves
 //       the loop over atom types early; that defect is reproduced only with
-//       `asbuilt` set.
+//       `asbuilt` set.  CLEMIN's as-built copy (:2650) also `exit`s its term loop at the
+//       first EX*R > 80 where the original skips that term only (GOTO 6); the
+//       original is restated.
 //
 // Pinning: the reference's tests/Re0001 holds an input/output pair of this step
 // (cluster_Re_bulk.i + atomic_Re.i -> mufftin_Re_bulk.d, NFORM=2, RELA densities,
