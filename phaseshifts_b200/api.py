@@ -396,7 +396,7 @@ _CAVPOT_FIELDS = (("type_off", np.int32), ("atom_off", np.int32), ("rc", np.floa
                   ("nh", np.int32), ("slab", np.int32), ("esht", np.float64), ("nform", np.int32))
 
 
-def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=False):
+def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=False, asbuilt=False):
     """The muffin-tin potential step of ``libphsh.cavpot`` (``libphsh.f:2070-2557``) for a batch of structures.
 
     ``structures``: sequence of dicts with ``spa`` (lattice constant, bohr), ``rc`` [3][3] (axis j = ``rc[j]``, in units of
@@ -413,6 +413,10 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=
     Returns a dict: ``mtz`` [S] (VHAR+VEX, what ``cavpot`` returns for a bulk run), ``vhar``, ``vex`` [S], ``npts`` [T],
     ``pot`` [T][421], ``type_off`` [S+1]; with ``diagnostics`` also ``vh``, ``vs``, ``vmad`` [T][250], the neighbour shells
     ``shell_ad/na/ia`` [T][30], ``ncon`` [T] and ``stats`` [S][4] (NINT, NPOINT, JRWS, NH after doubling).
+
+    ``asbuilt`` reproduces the neighbour search of the reference as built (``libphsh.f:3293-3398``: the loop over atom
+    types is left through ``exit`` where the original program continues), which starves every atom type after the first
+    of neighbour shells; the default follows the original ``phsh1.f``, which is what the reference's own fixture matches.
     """
     pk = structures if isinstance(structures, dict) else cavpot_pack(structures)
     keep = {k: np.ascontiguousarray(pk[k], dtype=dt).reshape(-1) for k, dt in _CAVPOT_FIELDS}
@@ -430,7 +434,7 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=
     if on_device:
         if diagnostics:
             raise ValueError("diagnostics are returned by the host entry point only")
-        return _cavpot_batch_device(keep, S, T, A, int(rho.shape[0]), int(device))
+        return _cavpot_batch_device(keep, S, T, A, int(rho.shape[0]), int(device), ASBUILT if asbuilt else 0)
     b = _lib.CavpotBatch()
     b.n_struct, b.n_types, b.n_atoms, b.max_types, b.max_atoms, b.n_dens = max(S, 0), T, A, 0, 0, int(rho.shape[0])
     for k, v in keep.items():
@@ -444,7 +448,7 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=
                    ncon=np.zeros(T, dtype=np.int32), stats=np.zeros((max(S, 0), 4), dtype=np.int32))
         for k in ("vh", "vs", "vmad", "shell_ad", "shell_na", "shell_ia", "ncon", "stats"):
             setattr(r, k, out[k].ctypes.data)
-    _lib.check(_lib.load().phsh_b200_cavpot_batch_host(C.byref(b), C.byref(r), 0, int(device)))
+    _lib.check(_lib.load().phsh_b200_cavpot_batch_host(C.byref(b), C.byref(r), ASBUILT if asbuilt else 0, int(device)))
     out["vhar"], out["vex"] = out["mtz2"][:, 0].copy(), out["mtz2"][:, 1].copy()
     out["mtz"] = out["vhar"] + out["vex"]
     out["type_off"] = keep["type_off"]
@@ -452,7 +456,7 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=
     return out
 
 
-def _cavpot_batch_device(keep, S, T, A, n_dens, device):
+def _cavpot_batch_device(keep, S, T, A, n_dens, device, flags=0):
     import torch
     dev = torch.device("cuda", device)
     d = {k: torch.from_numpy(v).to(dev) for k, v in keep.items()}
@@ -470,7 +474,7 @@ def _cavpot_batch_device(keep, S, T, A, n_dens, device):
     r.mtz, r.npts, r.pot, r.pot_stride = mtz.data_ptr(), npts.data_ptr(), pot.data_ptr(), 422
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(_lib.load().phsh_b200_cavpot_batch_device(C.byref(b), C.byref(r), 0, C.c_void_p(stream)))
+        _lib.check(_lib.load().phsh_b200_cavpot_batch_device(C.byref(b), C.byref(r), int(flags), C.c_void_p(stream)))
         # the inputs must outlive the launch: keep them referenced by the result until the stream has consumed them
     return dict(mtz=mtz[:, 0] + mtz[:, 1], vhar=mtz[:, 0], vex=mtz[:, 1], npts=npts, pot=pot, type_off=keep["type_off"],
                 _inputs=d)
@@ -489,9 +493,10 @@ def structures_to_phase_shifts(structures, rho, nx, energies_ryd, lmax, *, energ
     return delta, pots
 
 
-def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file, *, device=0):
+def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file, *, device=0,
+                asbuilt=False):
     """``libphsh.cavpot`` with its seven arguments (``libphsh.f:2070-2071``); returns the muffin-tin zero of a bulk run."""
-    opts = _lib.FileOpts(0, 0, 0, int(device))
+    opts = _lib.FileOpts(ASBUILT if asbuilt else 0, 0, 0, int(device))
     mtz = C.c_double(0.0)
     enc = lambda s: str(s).encode()
     _lib.check(_lib.load().phsh_b200_cavpot_file(enc(mtz_string), int(slab_flag), enc(atomic_file), enc(cluster_file),

@@ -20,7 +20,8 @@ it, otherwise it raises.  ``hb`` (a closed-form helper the f2py module also expo
 
 Environment switches (read at call time):
   PHSH_B200_DEVICE=<n>        CUDA device index (default 0)
-  PHSH_B200_ASBUILT=1         reproduce the as-built libphsh.f defects instead of phsh2.f
+  PHSH_B200_ASBUILT=1         reproduce the as-built libphsh.f defects (for cavpot: the neighbour
+                              search that leaves its atom-type loop early) instead of phsh2.f / phsh1.f
   PHSH_B200_REAL32=1          round the matching/averaging epilogue to REAL*4 like the Fortran declares it
   PHSH_B200_FAST=1            FMA-contracted integrator (not bit-faithful)
   PHSH_B200_MAX_ENERGIES=<n>  energy cap of PHSH_REL (reference: 250, libphsh.f:4642); 0 lifts it
@@ -97,7 +98,8 @@ def cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, outpu
     if _flag("PHSH_B200_CAVPOT_DELEGATE") and _delegate is not None and hasattr(_delegate, "cavpot"):
         return _delegate.cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file)
     return api.cavpot_file(_s(mtz_string), int(slab_flag), _s(atomic_file), _s(cluster_file), _s(mufftin_file),
-                           _s(output_file), _s(info_file), device=_int("PHSH_B200_DEVICE", 0))
+                           _s(output_file), _s(info_file), device=_int("PHSH_B200_DEVICE", 0),
+                           asbuilt=_flag("PHSH_B200_ASBUILT"))
 
 
 hartfock = _upstream("hartfock")  # libphsh.f:60    atomic charge densities (step 0)

@@ -132,7 +132,7 @@ def test_standin_module_surface(monkeypatch):
     seen = {}
     monkeypatch.setattr(api, "cavpot_file", lambda *a, **k: seen.update(cav=a, cavkw=k) or -1.5)
     assert libphsh.cavpot(b" -1.0 ", 1, "a.i ", "c.i", "m.d", "o.i", "info.txt") == -1.5
-    assert seen["cav"] == ("-1.0", 1, "a.i", "c.i", "m.d", "o.i", "info.txt") and seen["cavkw"] == {"device": 0}
+    assert seen["cav"] == ("-1.0", 1, "a.i", "c.i", "m.d", "o.i", "info.txt") and seen["cavkw"] == {"device": 0, "asbuilt": False}
     monkeypatch.setattr(api, "phsh_rel_file", lambda *a, **k: seen.update(args=a, kw=k))
     monkeypatch.setenv("PHSH_B200_MAX_ENERGIES", "0")
     monkeypatch.setenv("PHSH_B200_REAL32", "1")

@@ -238,6 +238,37 @@ def test_herman_skillman_and_clementi_densities_and_mixed_atomic_file(tmp_path):
     assert "POTE" in str(e.value)
 
 
+def test_asbuilt_neighbour_search(re_case, tmp_path, monkeypatch):
+    """PHSH_B200_ASBUILT: the neighbour search of libphsh.f as built (`exit` out of the loop over atom types).  Same lists
+    and potentials as the oracle's as-built restatement; the second atom type loses shells, and the golden mufftin.d (made
+    by the original program) is no longer reproduced."""
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api, libphsh
+    cl, _, rho, nx = re_case
+    ref = cio.cavpot(cl, rho, nx, real32=False, asbuilt=True)
+    good = cio.cavpot(cl, rho, nx, real32=False)
+    out = api.cavpot_batch([_struct(cl)], rho, nx, diagnostics=True, asbuilt=True)
+    assert np.array_equal(out["shell_ad"], ref["ad"]) and np.array_equal(out["shell_na"], ref["na"])
+    assert np.array_equal(out["shell_ia"], ref["ia"]) and list(out["ncon"]) == list(ref["ncon"])
+    assert ref["na"][1].sum() < good["na"][1].sum()
+    _check(out, 0, ref, 2)
+    c6 = cio.read_cluster(os.path.join(HERE, "golden", "examples", "cluster_C6Ni6.i"), real32=False)
+    blocks = cio.read_atomic(os.path.join(HERE, "golden", "examples", "atomic_C6Ni6.i"), 8, real32=False)
+    rho8 = np.zeros((8, 250))
+    nx8 = np.zeros(8, dtype=np.int32)
+    for i, b in enumerate(blocks):
+        rho8[i], nx8[i] = cio.density(b, real32=False)
+    ref8 = cio.cavpot(c6, rho8, nx8, real32=False, asbuilt=True)
+    out8 = api.cavpot_batch([_struct(c6)] * 150, rho8, nx8, diagnostics=True, asbuilt=True)   # 128-thread CTAs
+    assert np.array_equal(out8["shell_na"][-8:], ref8["na"]) and np.array_equal(out8["shell_ad"][:8], ref8["ad"])
+    _check(out8, 8 * 149, ref8, 8)
+    monkeypatch.setenv("PHSH_B200_ASBUILT", "1")
+    g = [str(tmp_path / n) for n in ("m.d", "b.i", "i.txt")]
+    libphsh.cavpot("", 0, os.path.join(RE, "atomic_Re.i"), os.path.join(RE, "cluster_Re_bulk.i"), *g)
+    gold, mine = _values(os.path.join(RE, "mufftin_Re_bulk.d")), _values(g[0])
+    assert np.abs(gold[0][3] - mine[0][3]).max() > 1e-2 or np.abs(gold[1][3] - mine[1][3]).max() > 1e-2
+
+
 def test_fine_sampling_grid_spans_many_passes(re_case):
     """NH = 24 -> 13824 sample points, ~3900 interstitial: the ordered compaction list is filled and drained dozens of times
     (128-thread CTAs in a 150-structure batch, 512-thread CTA alone); VHAR/VEX must stay bit-identical to the serial sum."""
