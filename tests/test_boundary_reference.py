@@ -37,9 +37,10 @@ def wired(monkeypatch, tmp_path, request):
 
         from oracle import cavpot_io as cio
 
-        def fake_cavpot_file(mtz_string, slab, atomic_file, cluster_file, mufftin_file, output_file, info_file, device=0):
+        def fake_cavpot_file(mtz_string, slab, atomic_file, cluster_file, mufftin_file, output_file, info_file, device=0,
+                             asbuilt=False):
             return cio.cavpot_file(mtz_string, slab, atomic_file, cluster_file, mufftin_file, output_file, info_file,
-                                   real32=False)[0]
+                                   real32=False, asbuilt=asbuilt)[0]
         monkeypatch.setattr(api, "cavpot_file", fake_cavpot_file)
 
     def replay_cavpot(mtz_string, slab, atomic_file, cluster_file, mufftin_file, output_file, info_file):
