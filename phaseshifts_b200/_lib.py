@@ -51,7 +51,8 @@ class CavpotBatch(C.Structure):
 class CavpotResult(C.Structure):
     _fields_ = [("mtz", C.c_void_p), ("npts", C.c_void_p), ("pot", C.c_void_p), ("pot_stride", C.c_long),
                 ("vh", C.c_void_p), ("vs", C.c_void_p), ("vmad", C.c_void_p), ("shell_ad", C.c_void_p),
-                ("shell_na", C.c_void_p), ("shell_ia", C.c_void_p), ("ncon", C.c_void_p), ("stats", C.c_void_p)]
+                ("shell_na", C.c_void_p), ("shell_ia", C.c_void_p), ("ncon", C.c_void_p), ("stats", C.c_void_p),
+                ("phase_clocks", C.c_void_p)]
 
 
 _dp = C.c_void_p  # raw addresses (host numpy or device tensor data_ptr)

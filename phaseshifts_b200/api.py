@@ -445,8 +445,9 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=
     if diagnostics:
         out.update(vh=np.zeros((T, 250)), vs=np.zeros((T, 250)), vmad=np.zeros((T, 250)), shell_ad=np.zeros((T, 30)),
                    shell_na=np.zeros((T, 30), dtype=np.int32), shell_ia=np.zeros((T, 30), dtype=np.int32),
-                   ncon=np.zeros(T, dtype=np.int32), stats=np.zeros((max(S, 0), 4), dtype=np.int32))
-        for k in ("vh", "vs", "vmad", "shell_ad", "shell_na", "shell_ia", "ncon", "stats"):
+                   ncon=np.zeros(T, dtype=np.int32), stats=np.zeros((max(S, 0), 4), dtype=np.int32),
+                   phase_clocks=np.zeros((max(S, 0), 8), dtype=np.int64))
+        for k in ("vh", "vs", "vmad", "shell_ad", "shell_na", "shell_ia", "ncon", "stats", "phase_clocks"):
             setattr(r, k, out[k].ctypes.data)
     _lib.check(_lib.load().phsh_b200_cavpot_batch_host(C.byref(b), C.byref(r), ASBUILT if asbuilt else 0, int(device)))
     out["vhar"], out["vex"] = out["mtz2"][:, 0].copy(), out["mtz2"][:, 1].copy()
