@@ -473,3 +473,16 @@ def test_error_behaviour(tmp_path):
     with pytest.raises(PhshB200Error):
         api.cavpot_batch([bad], rho, nx)
     assert api.cavpot_batch([], rho, nx)["pot"].shape == (0, 421)
+    # spheres that fill the whole cell: MTZ halves its sampling step until NH exceeds 256 and gives up -- the batch entry
+    # point hands back a NaN muffin-tin zero for that structure only, the file interface reports it
+    full = _struct(cl)
+    full["rmt"] = np.array([6.0, 6.0])
+    ok = _struct(cl)
+    r = api.cavpot_batch([ok, full, ok], rho, nx, diagnostics=True)
+    assert np.isnan(r["mtz"][1]) and np.isfinite(r["mtz"][[0, 2]]).all() and r["mtz"][0] == r["mtz"][2]
+    assert r["stats"][1][0] == 0 and r["stats"][1][3] > 256
+    big = tmp_path / "big.i"
+    big.write_text(open(ok_c).read().replace("2.6000", "6.0000"))
+    with pytest.raises(PhshB200Error) as e:
+        api.cavpot_file("", 0, ok_a, str(big), *outs)
+    assert "muffin-tin zero" in str(e.value)
