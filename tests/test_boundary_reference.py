@@ -73,6 +73,10 @@ def test_registry_and_module_seeding(wired):
     assert "b200" in B.DEFAULT_BACKENDS and isinstance(B.get_backend("B200"), wired[0])
     with pytest.raises(B.BackendError):
         B.get_backend("no-such-backend")
+    # the reference's other backends and their aliases are untouched by install() (backends.py:107-175)
+    assert isinstance(B.get_backend("bvh"), B.BVHBackend) and isinstance(B.get_backend("vanhove"), B.BVHBackend)
+    ee = B.get_backend("viperleed")
+    assert isinstance(ee, B.EEASiSSSBackend) and ee.mode == "viperleed" and B.get_backend("eeasisss").mode == "auto"
 
 
 def test_unchanged_wrapper_through_b200_backend_matches_golden_leedph(wired):
