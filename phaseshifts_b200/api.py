@@ -358,6 +358,26 @@ def cavpot_clemin_density(bases, states, device=0):
     return rho, int(nx.value)
 
 
+def cavpot_mesh(nform=2):
+    """The radial mesh the rows of ``cavpot_batch(...)["pot"]`` are tabulated on: Loucks' mesh ``exp(-8.8 + 0.05 (i-1))``,
+    250 points, for NFORM 0/1 (``libphsh.f:2107-2112``) or the relativistic program's 421-point grid
+    ``60 exp(0.03125 (i-421))`` for NFORM 2 (``:2439-2453``), built with the reference's own REAL*4-literal recurrences."""
+    import math
+    f = lambda v: float(np.float32(v))
+    if int(nform) == 2:
+        rm, dx = f(60.0), f(0.03125)
+        r = [rm * math.exp(dx * (1 - 421))]
+        step = math.exp(dx)
+        for _ in range(420):
+            r.append(step * r[-1])
+        return np.array(r)
+    x, r = f(-8.8), []
+    for _ in range(250):
+        r.append(math.exp(x))
+        x = x + f(0.05)
+    return np.array(r)
+
+
 def cavpot_pack(structures):
     """Flatten a sequence of structure dicts (see ``cavpot_batch``) into the ragged arrays of ``phsh_b200_cavpot_batch``.
     Lengths are multiplied by the lattice constant here, as ``CAVPOT`` does on input (``libphsh.f:2133-2137, 2209-2211``)."""

@@ -172,3 +172,10 @@ def test_split_phasout_needs_no_gpu(lib, tmp_path):
         from phaseshifts_b200 import PhshB200Error
         with pytest.raises(PhshB200Error):
             c.calculate()
+
+
+def test_cavpot_mesh_helpers():
+    from phaseshifts_b200 import api
+    lo, wa = api.cavpot_mesh(0), api.cavpot_mesh(2)
+    assert lo.shape == (250,) and wa.shape == (421,) and abs(wa[-1] - 60.0) < 1e-9 and abs(lo[0] - np.exp(-8.8)) < 1e-10
+    assert np.allclose(np.diff(np.log(wa)), 0.03125, atol=1e-12) and np.allclose(np.diff(np.log(lo)), 0.05, atol=1e-6)
