@@ -593,8 +593,9 @@ static inline void mad(std::vector<std::vector<Real>>& vmad, const std::vector<R
         gmin = std::min(gmin, rad(G[1][j], G[2][j], G[3][j]));
     }
     const Real lt = std::log(TEST);
-    Real fac1 = TEST * (lt * lt * lt * lt);  // TEST*ALOG(TEST)**4
-    Real rc4 = rcmin * rcmin * rcmin * rcmin, g4 = gmin * gmin * gmin * gmin;
+    // X**4 with an INTEGER exponent is (X*X)*(X*X) in gfortran's powi
+    Real fac1 = TEST * powi<Real>(lt, 4);  // TEST*ALOG(TEST)**4
+    Real rc4 = powi<Real>(rcmin, 4), g4 = powi<Real>(gmin, 4);
     Real fac2 = (lit<Real>(4.0f) * PI * rc4) / (av * g4);
     const Real al = std::exp(std::log(fac1 / fac2) / lit<Real>(6.0f));
     const int itr = 1 + ifix<Real>((al * rkmax - lt) / (al * rcmin));
