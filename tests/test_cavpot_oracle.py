@@ -166,3 +166,32 @@ def test_herman_skillman_and_clementi_forms(tmp_path):
     assert abs(np.trapezoid(rho_n[:nx_n], x[:nx_n]) - 10.0) < 0.05
     r32, n32 = cio.density(blocks[2], real32=True)
     assert n32 == nx_n and np.abs(r32 - rho_n).max() < 1e-4 * rho_n.max()
+
+
+def test_madelung_sums_give_the_rock_salt_constant():
+    """MAD has no fixture (unpinned); physics instead.  For point charges +-1 on the rock-salt lattice the spherical average
+    of the other ions' potential about a site is its value at the site (mean-value theorem), -+alpha/d Hartree with
+    alpha = 1.747565.  MAD tabulates 2*(own charge/r + that) - AMT in Rydberg, so the difference between the two sites
+    cancels the muffin-tin shift AMT: (V_Na(r) - 2/r) - (V_Cl(r) + 2/r) = -4 alpha/d inside the spheres.  The routine stops
+    its reciprocal-space sum where single terms fall below TEST = 1e-4; the sin(Gr)/(Gr) factor makes that converge to
+    a ripple of +-0.4 % around the exact value for r > 1 bohr, while towards the nucleus the truncated tail leaves up to 8 % (there -2Z/r dominates anyway)."""
+    cl = cio.read_cluster(os.path.join(RE, "cluster_Re_bulk.i"), real32=False)
+    blocks = cio.read_atomic(os.path.join(RE, "atomic_Re.i"), 2, real32=False)
+    rho = np.zeros((2, 250))
+    nx = np.zeros(2, dtype=np.int32)
+    for i, b in enumerate(blocks):
+        rho[i], nx[i] = cio.rela_density(b, real32=False)
+    a = 10.66
+    c = dict(spa=a, rc=np.array([[0.0, 0.5, 0.5], [0.5, 0.0, 0.5], [0.5, 0.5, 0.0]]), nr=2, nrr=np.array([1, 1], dtype=np.int32),
+             z=np.array([11.0, 17.0]), zc=np.array([1.0, -1.0]), rmt=np.array([2.2, 2.9]),
+             rk=np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]]), nform=0, alpha=0.7, nh=4)
+    for real32, tol in ((False, 2e-3), (True, 4e-3)):
+        r = cio.cavpot(c, rho, nx, real32=real32)
+        mesh = np.exp(np.float64(np.float32(-8.8)) + np.float64(np.float32(0.05)) * np.arange(250))
+        want = -4.0 * 1.747565 / (a / 2.0)
+        jm = int(min(r["jrmt"])) - 1
+        diff = (r["vmad"][0][:jm] - 2.0 / mesh[:jm]) - (r["vmad"][1][:jm] + 2.0 / mesh[:jm])
+        outer = mesh[:jm] > 1.0
+        assert np.abs(diff[outer] / want - 1.0).max() < tol, (real32, np.abs(diff[outer] / want - 1.0).max())
+        inner = (mesh[:jm] > 0.05) & ~outer
+        assert np.abs(diff[inner] / want - 1.0).max() < 0.09
