@@ -196,6 +196,11 @@ def conphas(phas, lmax=None, device=0):
     return out[0] if squeeze else out
 
 
+def trim(device=0):
+    """Return the scratch the library caches in its private memory pool on ``device`` to the driver."""
+    _lib.check(_lib.load().phsh_b200_trim(int(device)))
+
+
 def fp64_peak(device=0):
     """Measured FP64 DFMA peak (TFLOP/s) of one device and the SM clock it implies (MHz)."""
     lib = _lib.load()

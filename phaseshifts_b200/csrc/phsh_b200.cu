@@ -35,38 +35,74 @@ int cuda_fail(cudaError_t e, const char* what) {
                                                                          : PHSH_B200_ECUDA;
 }
 
+// ---- per-device context: private memory pool + recycled lanes (streams, events, pinned staging ring) -------------
+namespace {
+constexpr int kMaxDevices = 64;
+struct DeviceCtx {
+    std::mutex mu;
+    bool ready = false;
+    cudaMemPool_t pool = nullptr;
+    std::vector<HostLane*> idle;
+};
+DeviceCtx g_ctx[kMaxDevices];
+
+// context of `dev` (created on first use; lives as long as the process)
+int device_ctx(int dev, DeviceCtx** out) {
+    if (dev < 0 || dev >= kMaxDevices) {
+        set_error("device index %d not supported (max %d)", dev, kMaxDevices);
+        return PHSH_B200_EINVAL;
+    }
+    DeviceCtx& c = g_ctx[dev];
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.ready) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        PHSH_CUDA(cudaMemPoolCreate(&c.pool, &props));
+        const char* keep = getenv("PHSH_B200_POOL_KEEP_MB");
+        unsigned long long thr = (keep && keep[0] ? strtoull(keep, nullptr, 10) : 4096ull) << 20;
+        PHSH_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        c.ready = true;
+    }
+    *out = &c;
+    return 0;
+}
+}  // namespace
+
 int check_current_device() {
     int dev = 0;
     PHSH_CUDA(cudaGetDevice(&dev));
-    int major = 0;
-    PHSH_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    static int major_of[kMaxDevices];  // 0 = not asked yet
+    int major = (dev >= 0 && dev < kMaxDevices) ? major_of[dev] : 0;
+    if (!major) {
+        PHSH_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        if (dev >= 0 && dev < kMaxDevices) major_of[dev] = major;
+    }
     if (major != 10) {
         set_error("device %d has compute capability %d.x; this library is built for sm_100a (B200) only", dev, major);
         return PHSH_B200_ENODEV;
     }
-    static std::once_flag pool_once[64];
-    if (dev < 64)
-        std::call_once(pool_once[dev], [dev]() {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long thr = ~0ull;  // keep stream-ordered scratch cached between calls
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            }
-        });
     return 0;
 }
 
 int select_device(int device) {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        set_error("no CUDA device available (%s); libphsh_b200 has no CPU fallback",
-                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-        cudaGetLastError();
-        return PHSH_B200_ENODEV;
+    static int n_dev = -1;
+    if (n_dev <= 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            set_error("no CUDA device available (%s); libphsh_b200 has no CPU fallback",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+            cudaGetLastError();
+            return PHSH_B200_ENODEV;
+        }
+        n_dev = n;
     }
-    if (device < 0 || device >= n) {
-        set_error("device index %d out of range [0,%d)", device, n);
+    if (device < 0 || device >= n_dev) {
+        set_error("device index %d out of range [0,%d)", device, n_dev);
         return PHSH_B200_EINVAL;
     }
     PHSH_CUDA(cudaSetDevice(device));
@@ -75,8 +111,112 @@ int select_device(int device) {
 
 int DeviceBuf::alloc(size_t bytes, cudaStream_t stream) {
     s = stream;
-    PHSH_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, stream));
+    int dev = 0;
+    PHSH_CUDA(cudaGetDevice(&dev));
+    DeviceCtx* c = nullptr;
+    int rc = device_ctx(dev, &c);
+    if (rc) return rc;
+    PHSH_CUDA(cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, c->pool, stream));
     return 0;
+}
+
+int HostLane::event(cudaEvent_t* out) {
+    if (ev_next == ev.size()) {
+        cudaEvent_t e;
+        PHSH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev.push_back(e);
+    }
+    *out = ev[ev_next++];
+    return 0;
+}
+
+int HostLane::ensure_stage() {
+    for (int i = 0; i < kSlots; ++i) {
+        if (!stage[i]) PHSH_CUDA(cudaHostAlloc(&stage[i], kSlotBytes, cudaHostAllocDefault));
+        if (!stage_ev[i]) PHSH_CUDA(cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int HostLane::copy_back(void* dst, const void* src, size_t bytes, bool dst_pinned) {
+    if (dst_pinned || bytes < (256u << 10)) {  // small pageable copies: the driver's own staging is as good
+        PHSH_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sd));
+        return 0;
+    }
+    int rc = ensure_stage();
+    if (rc) return rc;
+    const size_t nchunk = (bytes + kSlotBytes - 1) / kSlotBytes;
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    // chunk k is DMA'd into slot k % kSlots; before a slot is reused its previous chunk is copied out on the host
+    for (size_t k = 0; k < nchunk + kSlots; ++k) {
+        if (k >= static_cast<size_t>(kSlots)) {
+            const size_t j = k - kSlots;  // drain chunk j
+            if (j < nchunk) {
+                PHSH_CUDA(cudaEventSynchronize(stage_ev[j % kSlots]));
+                memcpy(d + j * kSlotBytes, stage[j % kSlots], std::min(kSlotBytes, bytes - j * kSlotBytes));
+            }
+        }
+        if (k < nchunk) {
+            PHSH_CUDA(cudaMemcpyAsync(stage[k % kSlots], s + k * kSlotBytes, std::min(kSlotBytes, bytes - k * kSlotBytes),
+                                      cudaMemcpyDeviceToHost, sd));
+            PHSH_CUDA(cudaEventRecord(stage_ev[k % kSlots], sd));
+        }
+    }
+    return 0;
+}
+
+int StreamGuard::acquire() {
+    int dev = 0;
+    PHSH_CUDA(cudaGetDevice(&dev));
+    DeviceCtx* c = nullptr;
+    int rc = device_ctx(dev, &c);
+    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->idle.empty()) {
+            lane = c->idle.back();
+            c->idle.pop_back();
+        }
+    }
+    if (!lane) {
+        HostLane* l = new HostLane;
+        l->dev = dev;
+        cudaError_t e = cudaStreamCreateWithFlags(&l->sc, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l->sc2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l->sd, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            if (l->sc) cudaStreamDestroy(l->sc);
+            if (l->sc2) cudaStreamDestroy(l->sc2);
+            if (l->sd) cudaStreamDestroy(l->sd);
+            delete l;
+            return cuda_fail(e, "cudaStreamCreateWithFlags");
+        }
+        lane = l;
+    }
+    lane->ev_next = 0;
+    s = lane->sc;
+    return 0;
+}
+
+StreamGuard::~StreamGuard() {
+    if (!lane) return;
+    // nothing of this call may still be running when the caller's buffers go away
+    cudaStreamSynchronize(lane->sc);
+    cudaStreamSynchronize(lane->sc2);
+    cudaStreamSynchronize(lane->sd);
+    DeviceCtx& c = g_ctx[lane->dev];
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.idle.push_back(lane);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -126,10 +266,12 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
     const int lane_stride = packed ? NE : ((NE + block - 1) / block) * block;
     const int kmax = packed ? kpack : 1;
     const long ctas = (static_cast<long>(P) * lane_stride + block - 1) / block;
-    // At least ~8 waves of CTAs (148 SMs x 6 resident), so that the partially filled last wave costs little;
-    // smaller batches split the l range across CTAs (costly high-l groups first) to get there.
+    // At least ~64 waves of CTAs (148 SMs x 6 resident), so that the partially filled last wave costs little;
+    // smaller batches split the l range across CTAs (costly high-l groups first) to get there.  Measured on a
+    // 512-potential x 1000-energy shard (the 8-GPU share of the C4 sweep): 1-2 l-groups 27.5 ms, 4: 26.8, 8: 26.5,
+    // 16: 26.3 ms = 99.4 % of the per-potential rate of the full 4096-potential launch.
     int lgroups = 1;
-    const long target = 148L * kRelMinBlocks * 8;
+    const long target = 148L * kRelMinBlocks * 64;
     while (ctas * lgroups < target && lgroups < L1) ++lgroups;
     // still short of CTAs with one l per CTA: split the two kappa of an l as well (KSPLIT kernel)
     const int nitems = 2 * L1 - 1;  // kappa items per lane
@@ -281,42 +423,37 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
     if (rc) return rc;
     if (P == 0 || NE == 0) return 0;
     if (!e_l) e_l = e_l0;
-    // Three streams: slabs alternate between two compute streams (`sc`, `sc2`) so that the draining tail of one
-    // slab's integrator overlaps the head of the next, and results are copied on `sd`, so that the D2H of slab k
-    // overlaps the integration of slab k+1.
-    struct Streams {
-        cudaStream_t sc = nullptr, sc2 = nullptr, sd = nullptr;
-        std::vector<cudaEvent_t> ev;
-        ~Streams() {
-            for (auto e : ev) cudaEventDestroy(e);
-            if (sc) cudaStreamDestroy(sc);
-            if (sc2) cudaStreamDestroy(sc2);
-            if (sd) cudaStreamDestroy(sd);
-        }
-    } S;
-    PHSH_CUDA(cudaStreamCreateWithFlags(&S.sc, cudaStreamNonBlocking));
-    PHSH_CUDA(cudaStreamCreateWithFlags(&S.sc2, cudaStreamNonBlocking));
-    PHSH_CUDA(cudaStreamCreateWithFlags(&S.sd, cudaStreamNonBlocking));
-    cudaStream_t st = S.sc;
+    // Three streams of a recycled lane: slabs alternate between two compute streams (`sc`, `sc2`) so that the draining
+    // tail of one slab's integrator overlaps the head of the next, and results are copied back on `sd`, so that the
+    // D2H of slab k overlaps the integration of slab k+1.  Every kernel of the call is enqueued BEFORE the first copy
+    // back, so a pageable destination (whose copies block the host) does not hold up later slabs either.
     const int L1 = opts->lsm + 1;
     const long ps = (pot_stride + 1) & ~1L;  // device copy padded to an even stride
     const size_t n_e = e_stride ? static_cast<size_t>(P) * e_stride : static_cast<size_t>(NE);
-    // Slabs of potentials in a geometric schedule (P/2, P/4, ... , P/32, P/32): only the last, small slab's D2H
-    // is exposed, while the big early slabs keep the wave-quantisation loss of the integrator low
-    // (measured on C4: e2e/device-resident = 0.992 with 3 halvings, 0.997 with 4-6).
+    const size_t per_pot = static_cast<size_t>(NE) * L1;
+    // Slabs of potentials in a geometric schedule (P/2, P/4, ...): only the last, small slab's D2H is exposed, while
+    // the big early slabs keep the wave-quantisation loss of the integrator low.  Halving stops once the remainder's
+    // results are a few MB (tens of microseconds of PCIe time).
     std::vector<int> slabs;
     {
-        static const int levels = getenv("PHSH_B200_SLAB_LEVELS") ? atoi(getenv("PHSH_B200_SLAB_LEVELS")) : 5;
+        static const int levels = getenv("PHSH_B200_SLAB_LEVELS") ? atoi(getenv("PHSH_B200_SLAB_LEVELS")) : 9;
+        static const size_t min_bytes =
+            static_cast<size_t>(getenv("PHSH_B200_SLAB_MIN_MB") ? atoi(getenv("PHSH_B200_SLAB_MIN_MB")) : 2) << 20;
         int left = P;
-        for (int k = 0; k < levels && left > 256; ++k) {
+        for (int k = 0; k < levels && left > 1; ++k) {
+            const size_t left_bytes = static_cast<size_t>(left) * per_pot * sizeof(double);
+            if (left_bytes <= min_bytes) break;
             const int n = (left + 1) / 2;
             slabs.push_back(n);
             left -= n;
         }
         if (left > 0) slabs.push_back(left);
     }
-    const size_t per_pot = static_cast<size_t>(NE) * L1;
-    DeviceBuf d_pot, d_jri, d_e0, d_e1, d_delta, d_raw, d_cnt;
+    DeviceBuf d_pot, d_jri, d_e0, d_e1, d_delta, d_raw, d_cnt;  // before the lease: released after it has drained
+    StreamGuard S;
+    if ((rc = S.acquire())) return rc;
+    HostLane& ln = *S.lane;
+    cudaStream_t st = ln.sc;
     if ((rc = d_pot.alloc(static_cast<size_t>(P) * ps * sizeof(double), st))) return rc;
     if ((rc = d_jri.alloc(static_cast<size_t>(P) * sizeof(int), st))) return rc;
     if ((rc = d_e0.alloc(n_e * sizeof(double), st))) return rc;
@@ -332,40 +469,58 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
     PHSH_CUDA(cudaMemcpyAsync(d_e1.p, e_l, n_e * sizeof(double), cudaMemcpyHostToDevice, st));
     PHSH_CUDA(cudaMemsetAsync(d_cnt.p, 0, 4 * sizeof(unsigned long long), st));
     cudaEvent_t ready;  // inputs are on the device
-    PHSH_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    S.ev.push_back(ready);
+    if ((rc = ln.event(&ready))) return rc;
     PHSH_CUDA(cudaEventRecord(ready, st));
-    PHSH_CUDA(cudaStreamWaitEvent(S.sc2, ready, 0));
+    PHSH_CUDA(cudaStreamWaitEvent(ln.sc2, ready, 0));
+    std::vector<cudaEvent_t> done(slabs.size());
     int p0 = 0;
     for (size_t si = 0; si < slabs.size(); p0 += slabs[si], ++si) {
         const int n = slabs[si];
-        cudaStream_t st = (si & 1) ? S.sc2 : S.sc;
+        cudaStream_t sk = (si & 1) ? ln.sc2 : ln.sc;
         double* raw = static_cast<double*>(d_raw.p) + static_cast<size_t>(p0) * per_pot * 2;
         double* dl = static_cast<double*>(d_delta.p) + static_cast<size_t>(p0) * per_pot;
         rc = phsh_b200_rel_batch_device(static_cast<double*>(d_pot.p) + static_cast<size_t>(p0) * ps, ps,
                                         static_cast<int*>(d_jri.p) + p0, n,
                                         static_cast<double*>(d_e0.p) + (e_stride ? static_cast<size_t>(p0) * e_stride : 0),
                                         static_cast<double*>(d_e1.p) + (e_stride ? static_cast<size_t>(p0) * e_stride : 0),
-                                        e_stride, NE, opts, dl, raw, static_cast<unsigned long long*>(d_cnt.p), st);
+                                        e_stride, NE, opts, dl, raw, static_cast<unsigned long long*>(d_cnt.p), sk);
         if (rc) return rc;
-        cudaEvent_t ev;
-        PHSH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        S.ev.push_back(ev);
-        PHSH_CUDA(cudaEventRecord(ev, st));
-        PHSH_CUDA(cudaStreamWaitEvent(S.sd, ev, 0));
-        PHSH_CUDA(cudaMemcpyAsync(delta + static_cast<size_t>(p0) * per_pot, dl, static_cast<size_t>(n) * per_pot * sizeof(double),
-                                  cudaMemcpyDeviceToHost, S.sd));
-        if (kappa_out)
-            PHSH_CUDA(cudaMemcpyAsync(kappa_out + static_cast<size_t>(p0) * per_pot * 2, raw,
-                                      static_cast<size_t>(n) * per_pot * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.sd));
+        if ((rc = ln.event(&done[si]))) return rc;
+        PHSH_CUDA(cudaEventRecord(done[si], sk));
+    }
+    const bool pinned_delta = host_pointer_is_pinned(delta);
+    const bool pinned_kappa = kappa_out ? host_pointer_is_pinned(kappa_out) : true;
+    p0 = 0;
+    for (size_t si = 0; si < slabs.size(); p0 += slabs[si], ++si) {
+        const int n = slabs[si];
+        const double* raw = static_cast<double*>(d_raw.p) + static_cast<size_t>(p0) * per_pot * 2;
+        const double* dl = static_cast<double*>(d_delta.p) + static_cast<size_t>(p0) * per_pot;
+        PHSH_CUDA(cudaStreamWaitEvent(ln.sd, done[si], 0));
+        if ((rc = ln.copy_back(delta + static_cast<size_t>(p0) * per_pot, dl, static_cast<size_t>(n) * per_pot * sizeof(double),
+                               pinned_delta)))
+            return rc;
+        if (kappa_out &&
+            (rc = ln.copy_back(kappa_out + static_cast<size_t>(p0) * per_pot * 2, raw,
+                               static_cast<size_t>(n) * per_pot * 2 * sizeof(double), pinned_kappa)))
+            return rc;
     }
     unsigned long long cnt[4] = {0, 0, 0, 0};
-    PHSH_CUDA(cudaStreamSynchronize(S.sc2));
+    PHSH_CUDA(cudaStreamSynchronize(ln.sc2));
     PHSH_CUDA(cudaMemcpyAsync(cnt, d_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, st));
     PHSH_CUDA(cudaStreamSynchronize(st));
-    PHSH_CUDA(cudaStreamSynchronize(S.sd));
+    PHSH_CUDA(cudaStreamSynchronize(ln.sd));
     if (counters)
         for (int i = 0; i < 4; ++i) counters[i] += cnt[i];
+    return 0;
+}
+
+int phsh_b200_trim(int device) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    DeviceCtx* c = nullptr;
+    if ((rc = device_ctx(device, &c))) return rc;
+    PHSH_CUDA(cudaDeviceSynchronize());
+    PHSH_CUDA(cudaMemPoolTrimTo(c->pool, 0));
     return 0;
 }
 
@@ -387,13 +542,14 @@ int phsh_b200_conphas_device(const double* phas, int P, int NE, int L, int lmax,
 int phsh_b200_conphas_host(const double* phas, int P, int NE, int L, int lmax, double* out, int device) {
     int rc = select_device(device);
     if (rc) return rc;
-    if (P <= 0 || NE <= 0 || L < 1) return P < 0 || NE < 0 || L < 1 ? PHSH_B200_EINVAL : 0;
-    cudaStream_t st;
-    PHSH_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    struct StreamGuard {
-        cudaStream_t s;
-        ~StreamGuard() { cudaStreamDestroy(s); }
-    } guard{st};
+    if (P < 0 || NE < 0 || L < 1) {
+        set_error("bad sizes: P=%d NE=%d L=%d", P, NE, L);
+        return PHSH_B200_EINVAL;
+    }
+    if (P == 0 || NE == 0) return 0;
+    StreamGuard guard;
+    if ((rc = guard.acquire())) return rc;
+    cudaStream_t st = guard.s;
     const size_t bytes = static_cast<size_t>(P) * NE * L * sizeof(double);
     DeviceBuf a, b;
     if ((rc = a.alloc(bytes, st))) return rc;

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/phsh_b200.h"
 
@@ -23,7 +24,9 @@ int cuda_fail(cudaError_t e, const char* what);
 int select_device(int device);
 int check_current_device();
 
-// stream-ordered scratch that is retained by the default mempool between calls
+// stream-ordered scratch from the library's PRIVATE per-device memory pool (never the device's default pool, which
+// the embedding process -- e.g. torch's allocator -- may be sharing).  The pool keeps up to PHSH_B200_POOL_KEEP_MB
+// (default 4096) cached between calls; phsh_b200_trim() hands everything back to the driver.
 struct DeviceBuf {
     void* p = nullptr;
     cudaStream_t s = nullptr;
@@ -31,6 +34,37 @@ struct DeviceBuf {
         if (p) cudaFreeAsync(p, s);
     }
     int alloc(size_t bytes, cudaStream_t stream);
+};
+
+// What a "_host" / "_file" entry point needs besides device memory: streams, events and (for pageable host buffers)
+// a pinned staging ring.  Created once per device and recycled between calls; concurrent host threads each get a
+// lane of their own, so the entry points stay re-entrant.
+struct HostLane {
+    static constexpr int kSlots = 4;
+    static constexpr size_t kSlotBytes = 8u << 20;
+    int dev = -1;
+    cudaStream_t sc = nullptr, sc2 = nullptr, sd = nullptr;  // two compute streams + one copy-back stream
+    std::vector<cudaEvent_t> ev;                              // recycled, timing disabled
+    size_t ev_next = 0;
+    void* stage[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    int event(cudaEvent_t* out);  // next recycled event of this call
+    int ensure_stage();           // allocates the pinned ring on first use
+    // dst (HOST, pinned or pageable) <- src (DEVICE), ordered after everything already enqueued on `sd`.  Pinned
+    // destinations: one asynchronous copy.  Pageable destinations: chunks through the pinned ring with the host
+    // memcpy of chunk k overlapping the DMA of chunk k+1; returns when the bytes are in dst.
+    int copy_back(void* dst, const void* src, size_t bytes, bool dst_pinned);
+};
+bool host_pointer_is_pinned(const void* p);
+
+// RAII lease of a lane of the CURRENT device (call select_device first).  The destructor drains the lane's three
+// streams before the lane is handed back, so an early error return can never leave work in flight on buffers that
+// are about to be released: declare the DeviceBufs of a multi-stream entry point BEFORE its lease.
+struct StreamGuard {
+    cudaStream_t s = nullptr;  // = lane->sc
+    HostLane* lane = nullptr;
+    int acquire();
+    ~StreamGuard();
 };
 
 }  // namespace phsh

@@ -34,11 +34,23 @@ def rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def _require_group(world: int, what: str):
+    """A gather over world>1 ranks needs an initialised process group: the RANK/WORLD_SIZE environment alone (e.g. under
+    torchrun before ``init_process_group``) would otherwise hand back one rank's shard as if it were the whole array."""
+    d = _dist()
+    if world > 1 and d is None:
+        raise RuntimeError("%s: WORLD_SIZE=%d but torch.distributed is not initialised -- call "
+                           "torch.distributed.init_process_group first, or pass gather=False" % (what, world))
+    return d
+
+
 def gather_blocks(local, P: int, group=None):
     """All-gather the per-rank blocks ``local`` [P_r, ...] (torch tensor, cpu or cuda) into [P, ...] on every rank."""
     import torch
     d = _dist()
     if d is None:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            _require_group(int(os.environ["WORLD_SIZE"]), "gather_blocks")
         return local
     rank, world = d.get_rank(group), d.get_world_size(group)
     sizes = [shard_range(P, r, world)[1] - shard_range(P, r, world)[0] for r in range(world)]
@@ -61,6 +73,8 @@ def phsh_rel_sweep(pot, jri, energies_ryd, lmax, *, gather=True, compute=None, g
     """
     import torch
     rank, world = rank_world()
+    if gather:
+        _require_group(world, "phsh_rel_sweep(gather=True)")
     pot = np.asarray(pot)
     P = pot.shape[0]
     jri = np.broadcast_to(np.asarray(jri, dtype=np.int32), (P,))
@@ -92,7 +106,9 @@ def phsh_rel_sweep(pot, jri, energies_ryd, lmax, *, gather=True, compute=None, g
 def _gather_ragged(local, sizes, group=None):
     """All-gather blocks whose row counts ``sizes[rank]`` every rank can work out from the (replicated) inputs."""
     import torch
-    d = _dist()
+    d = _require_group(len(sizes), "_gather_ragged")
+    if d is None:  # a single rank: nothing to exchange
+        return local
     rank, world = d.get_rank(group), d.get_world_size(group)
     if local.shape[0] != sizes[rank]:
         raise ValueError("rank %d holds %d rows, expected %d" % (rank, local.shape[0], sizes[rank]))
@@ -114,6 +130,8 @@ def cavpot_sweep(structures, rho, nx, *, gather=True, compute=None, group=None):
     """
     import torch
     rank, world = rank_world()
+    if gather:
+        _require_group(world, "cavpot_sweep(gather=True)")
     S = len(structures)
     a, b = shard_range(S, rank, world)
     if compute is None:

@@ -129,3 +129,26 @@ def test_two_rank_cavpot_sweep_equals_single_rank(tmp_path, S):
         assert np.array_equal(z["pot"], ref["pot"]) and z["type_off"][-1] == ref["pot"].shape[0]
         a, b = z["rng"]
         assert np.array_equal(z["lmtz"], ref["mtz"][a:b])
+
+
+def test_gather_without_process_group_raises(monkeypatch):
+    """WORLD_SIZE>1 in the environment but no init_process_group: a gather must fail loudly instead of returning one
+    rank's shard as the whole array (and cavpot_sweep must not crash on a missing group object)."""
+    from phaseshifts_b200 import distributed as D
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    pot = np.ones((4, 16))
+    calls = []
+
+    def compute(p_, j_, e_, l_, **kw):
+        calls.append(p_.shape[0])
+        return np.zeros((p_.shape[0], 3, l_ + 1))
+
+    with pytest.raises(RuntimeError, match="not initialised"):
+        D.phsh_rel_sweep(pot, 16, np.array([1.0, 2.0, 3.0]), 2, compute=compute)
+    with pytest.raises(RuntimeError, match="not initialised"):
+        D.cavpot_sweep([dict(nrr=[1])] * 4, None, None, compute=lambda *a: None)
+    assert calls == []
+    # without a gather the env-derived shard is legitimate
+    local, (a, b) = D.phsh_rel_sweep(pot, 16, np.array([1.0, 2.0, 3.0]), 2, compute=compute, gather=False)
+    assert (a, b) == (0, 2) and local.shape == (2, 3, 3)
