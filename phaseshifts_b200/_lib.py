@@ -97,6 +97,8 @@ _SIGNATURES = {
     "phsh_b200_selftest_cavpot": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),
     "phsh_b200_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "phsh_b200_selftest_div075": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),
+    "phsh_b200_selftest_divfast": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong),
+                                             C.POINTER(C.c_ulonglong), C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

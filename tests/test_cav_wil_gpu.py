@@ -94,3 +94,47 @@ def test_exact_division_by_0p75_selftest():
         bad = ctypes.c_ulonglong(123)
         _lib.check(lib.phsh_b200_selftest_div075(100_000_000, seed, ctypes.byref(bad), 0))
         assert bad.value == 0
+
+
+def test_cav_exact_division_pass_gives_the_same_bits(oracle, monkeypatch):
+    """The Numerov chain divides with the branch-free fast path of the IEEE division and only records whether a divisor
+    or quotient ever left its validity window; if one did, that l is repeated with __ddiv_rn.  PHSH_B200_CAV_EXACT=1
+    forces the repeat pass: identical bits."""
+    from phaseshifts_b200 import api, workloads
+    w = workloads.c2_oxide(ne=257, nl=16)
+    fast = api.phsh_cav_batch(w["V"], w["RX"], w["ntab"], w["rmt"], w["e_ryd"], NL=16)
+    monkeypatch.setenv("PHSH_B200_CAV_EXACT", "1")
+    exact = api.phsh_cav_batch(w["V"], w["RX"], w["ntab"], w["rmt"], w["e_ryd"], NL=16)
+    assert np.array_equal(fast, exact)
+    monkeypatch.delenv("PHSH_B200_CAV_EXACT")
+    # operands outside the window make the repeat pass run for real: a barrier V = 4800/r^2 puts the Numerov divisor
+    # 1-DAC*GAM (DAC = 1/4800.0008) within 2**-8 of zero over much of the grid
+    V = w["V"].copy()
+    V[0] = 4800.0 / np.maximum(w["RX"][0] ** 2, 1e-30)
+    got = api.phsh_cav_batch(V, w["RX"], w["ntab"], w["rmt"], w["e_ryd"][:64], NL=40)
+    ref, _ = oracle.cav_batch(V, w["RX"], w["ntab"], w["rmt"], w["e_ryd"][:64], NL=40)
+    both = np.isfinite(got) & np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    # phases are compared modulo pi: with |A/B| ~ 1e300 the branch of atan is decided by the last bit of B
+    d = np.abs(got[both] - ref[both])
+    assert np.minimum(d, np.abs(d - np.pi)).max() <= 1e-6
+    for r in (1.8e-4, 1.9e-4):  # JR = 5, 6: the chain is 3-4 steps long and the fit reads the starting values
+        rmt = np.full_like(w["rmt"], r)
+        got = api.phsh_cav_batch(w["V"], w["RX"], w["ntab"], rmt, w["e_ryd"][:64], NL=6)
+        ref, _ = oracle.cav_batch(w["V"], w["RX"], w["ntab"], rmt, w["e_ryd"][:64], NL=6)
+        assert np.isfinite(got).all() and np.isfinite(ref).all()
+        assert (np.abs(got - ref) <= 1e-9 * np.abs(ref)).all()  # the phases themselves are 1e-8 .. 1e-60 here
+
+
+def test_fast_division_selftest():
+    """The tracked quotient of cav_ps_kernel against __ddiv_rn, bit for bit, on 4e8 operand pairs straddling the window;
+    most of them must actually have been inside it."""
+    import ctypes
+    from phaseshifts_b200 import _lib
+    lib = _lib.load()
+    for seed in (1, 2):
+        bad, used = ctypes.c_ulonglong(123), ctypes.c_ulonglong(0)
+        n = 200_000_000
+        _lib.check(lib.phsh_b200_selftest_divfast(n, seed, ctypes.byref(bad), ctypes.byref(used), 0))
+        assert bad.value == 0
+        assert used.value > 0.5 * n
