@@ -29,7 +29,7 @@ def build(force: bool = False) -> str:
     """Compile oracle/libphsh_oracle.so with the committed Makefile."""
     so = os.path.join(_HERE, "libphsh_oracle.so")
     srcs = [os.path.join(_HERE, f) for f in ("phsh_oracle_capi.cpp", "phsh_oracle.hpp", "cavpot_oracle_capi.cpp",
-                                             "cavpot_oracle.hpp", "Makefile")]
+                                             "cavpot_oracle.hpp", "hartfock_oracle_capi.cpp", "hartfock_oracle.hpp", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), check=True)
     return so

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import numpy as np, torch
 from phaseshifts_b200 import api, workloads
 w = workloads.c2_oxide()
-for P in (4, 64, 128, 256, 512, 1024, 4096, 256, 64):
+for P in ([int(x) for x in sys.argv[1:]] or (4, 64, 128, 256, 512, 1024, 4096, 256, 64)):
     rep = P // 4
     V = torch.from_numpy(np.tile(w["V"], (rep, 1))).cuda(); RX = torch.from_numpy(np.tile(w["RX"], (rep, 1))).cuda()
     ntab = np.tile(w["ntab"], rep); rmt = np.tile(w["rmt"], rep)
