@@ -55,6 +55,12 @@ class CavpotResult(C.Structure):
                 ("phase_clocks", C.c_void_p)]
 
 
+class HartfockAtom(C.Structure):
+    _fields_ = [("z", C.c_double), ("nr", C.c_int), ("rel", C.c_double), ("alfa", C.c_double), ("iuflag", C.c_int),
+                ("nel", C.c_int), ("ratio", C.c_double), ("etol", C.c_double), ("xnum", C.c_double),
+                ("orbitals", C.c_void_p)]
+
+
 _dp = C.c_void_p  # raw addresses (host numpy or device tensor data_ptr)
 _SIGNATURES = {
     "phsh_b200_last_error": (C.c_char_p, []),
@@ -94,6 +100,9 @@ _SIGNATURES = {
                                                   C.POINTER(C.c_int), C.c_int]),
     "phsh_b200_cavpot_file": (C.c_int, [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p,
                                         C.POINTER(FileOpts), C.POINTER(C.c_double)]),
+    "phsh_b200_hartfock_batch_host": (C.c_int, [C.POINTER(HartfockAtom), C.c_int, _dp, C.c_long, _dp, _dp, _dp, C.c_int,
+                                                C.c_int, C.c_int]),
+    "phsh_b200_hartfock_file": (C.c_int, [C.c_char_p, C.POINTER(FileOpts)]),
     "phsh_b200_selftest_cavpot": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),
     "phsh_b200_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "phsh_b200_selftest_div075": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),

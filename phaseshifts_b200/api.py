@@ -537,3 +537,42 @@ def selftest_cavpot(n=1 << 22, seed=1, device=0):
     bad = C.c_ulonglong(0)
     _lib.check(_lib.load().phsh_b200_selftest_cavpot(int(n), int(seed), C.byref(bad), int(device)))
     return int(bad.value)
+
+
+def hartfock_batch(atoms, *, history_cap=64, asbuilt=False, device=0):
+    """Self-consistent atomic charge densities for a batch of atoms (``libphsh.f:60-2068``, one CTA per atom).
+
+    ``atoms``: list of dicts ``z, nr[, rel=1, alfa=0, iuflag=0, ratio=0.5, etol=0.0005, xnum=100], orbitals`` with
+    ``orbitals`` = rows ``(n, l, m, -j, spin, occupation)`` as in the records of hartfock's ``a`` command.
+    Returns a list of dicts ``rho [nr], ev [nel], etot, scf_iterations, mixing_too_strong, rmin, rmax, history``.
+    """
+    lib = _lib.load()
+    n = len(atoms)
+    arr = (_lib.HartfockAtom * max(n, 1))()
+    keep = []
+    nrmax = 8
+    for k, a in enumerate(atoms):
+        orb = np.ascontiguousarray(np.asarray(a["orbitals"], dtype=np.float64).reshape(-1, 6))
+        keep.append(orb)
+        arr[k] = _lib.HartfockAtom(float(a["z"]), int(a["nr"]), float(a.get("rel", 1.0)), float(a.get("alfa", 0.0)),
+                                   int(a.get("iuflag", 0)), orb.shape[0], float(a.get("ratio", 0.5)),
+                                   float(a.get("etol", 0.0005)), float(a.get("xnum", 100.0)), orb.ctypes.data)
+        nrmax = max(nrmax, int(a["nr"]))
+    rho = np.zeros((max(n, 1), nrmax))
+    ev, info, hist = np.zeros((max(n, 1), 33)), np.zeros((max(n, 1), 8)), np.zeros((max(n, 1), 2 * history_cap))
+    _lib.check(lib.phsh_b200_hartfock_batch_host(arr, n, _ptr(rho), nrmax, _ptr(ev), _ptr(info), _ptr(hist), int(history_cap),
+                                                 ASBUILT if asbuilt else 0, int(device)))
+    out = []
+    for k, a in enumerate(atoms):
+        it = int(info[k, 1])
+        out.append(dict(rho=rho[k, : int(a["nr"])].copy(), ev=ev[k, : keep[k].shape[0]].copy(), etot=float(info[k, 0]),
+                        scf_iterations=it, mixing_too_strong=bool(info[k, 2]), rmin=float(info[k, 4]), rmax=float(info[k, 5]),
+                        history=hist[k, : 2 * min(it, history_cap)].reshape(-1, 2).copy()))
+    return out
+
+
+def hartfock_file(input_file, *, asbuilt=False, device=0):
+    """``libphsh.hartfock(input_file)``: runs the command stream (i, d, x, u, a, w, q) on the GPU and writes the ``w``
+    files relative to the current directory, like the Fortran (``libphsh.f:60-279``, ``hfdisk`` :1846-1917)."""
+    opts = _lib.FileOpts(ASBUILT if asbuilt else 0, 0, 0, int(device))
+    _lib.check(_lib.load().phsh_b200_hartfock_file(str(input_file).encode(), C.byref(opts)))

@@ -14,6 +14,7 @@
 #include "phsh_cav.cuh"
 #include "phsh_wil.cuh"
 #include "phsh_cavpot.cuh"
+#include "phsh_hartfock.cuh"
 
 namespace phsh {
 
@@ -615,3 +616,4 @@ int phsh_b200_fp64_peak(int device, double* tflops, double* sm_clock_mhz_est) {
 
 #include "phsh_cav_wil_abi.inc"
 #include "phsh_cavpot_abi.inc"
+#include "phsh_hartfock_abi.inc"

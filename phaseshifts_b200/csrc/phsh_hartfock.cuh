@@ -1,0 +1,661 @@
+// phsh_hartfock.cuh -- sm_100a kernel for the atomic charge-density step (`libphsh.hartfock`).
+//
+// Reference being replaced (phaseshifts/lib/libphsh.f): abinitio :282-369, atsolve :372-440, getpot :443-739,
+// elsolve :742-793, augment :796-841, setqmm :844-931, integ :992-1165, the density of hfdisk :1889-1896; driven from
+// phaseshifts/atorb.py:1095-1209.  The whole self-consistency loop of one atom runs inside ONE kernel launch.
+//
+// Design.  One CTA per atom (a batch = the elements of a structure, or of many).  The reference is a strictly serial
+// program; what parallelism it has is
+//   * the orbitals of one SCF iteration are independent (22 for Re): one WARP per orbital;
+//   * elsolve finds each eigenvalue by ~46 bisection steps, each an outward Numerov sweep whose outcome is one of
+//     {too low, too high, converged}: the 31 energies of the next FIVE bisection levels are a fixed binary tree of
+//     midpoints, so the 32 lanes of the warp integrate them concurrently and the warp then walks the tree with the
+//     actual outcomes -- the visited energies, in order, are exactly the serial bisection's, five levels per round;
+//   * getpot's radial integrals are running sums along r (order matters for bits), but independent between the ~700
+//     (orbital pair, multipole) terms: one THREAD per term scans r and stores its contribution, then one thread per
+//     (orbital, r) adds the contributions in the reference's order of the pair loops.
+// Everything order-dependent keeps the reference's order, every operation is the IEEE double operation of the Fortran
+// statement (file compiled with -fmad=false, __ddiv_rn, correctly rounded sqrt), and every transcendental of the
+// Hartree-Fock path (the log grid, r**k, the power-law start of integ) is tabulated on the host with libm: the
+// eigenvalues, orbitals and charge density are bit-identical to the CPU restatement (oracle/hartfock_oracle.hpp).
+// Exceptions: the total energy (information only, never fed back) is summed per term and then over terms; the local
+// exchange-correlation mode (alfa != 0: pow/log of exchcorr on the device) agrees to rounding, not bit for bit.
+// Bound: latency of dependent FP64 divisions (a serial recurrence per lane) -- nothing here approaches a roofline, the
+// point of the kernel is that the drop-in no longer needs a host Fortran build for its first step.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace phsh {
+
+constexpr int kHfMaxOrb = 33;     // iorbs (libphsh.f:63)
+constexpr int kHfMaxNr = 4000;    // nrmax
+constexpr int kHfMaxEvents = 64;  // rescalings of one outward sweep kept for the parallel fix-up
+constexpr int kHfMaxStack = 48;   // sweeps of one bisection whose phi entries survive (see elsolve below)
+
+struct HfTerm {   // one (i, j, la) term of getpot's pair loops, in the reference's order
+    int i, j, la, kind;  // kind 0 = direct Coulomb (:473-538), 1 = exchange (:548-613); i, j 0-based
+    double ri, rj, rc;
+};
+
+struct HfProblem {  // one atom; every pointer is a DEVICE pointer into this atom's workspace
+    int nr, nel, nterms, iuflag, max_iter, asbuilt;
+    double z, rel, alfa, ratio, etol, xnum, dl;
+    double pw12[kHfMaxOrb];  // (r(2)/r(1))**(ss-1/2) of integ :1052 (ss = l+1 without relativity, else sqrt(1-(z alpha)^2))
+    int no[kHfMaxOrb], nl[kHfMaxOrb], is[kHfMaxOrb];
+    double xnj[kHfMaxOrb], occ[kHfMaxOrb];
+    const double *r, *dr, *r2, *rpower;  // [nr], rpower [8][nr]
+    double *phe, *orb, *v, *xm1, *xm2, *phi2;  // [nel][nr]
+    double *contrib;                            // [nterms][2][nr]
+    const HfTerm* terms;
+    const int* upd_off;   // [nel+1]
+    const int* upd;       // entries term*2+slot, per orbital in application order
+    double *rho, *ev, *ek;  // outputs [nr], [nel], [nel]
+    double* info;           // [8] etot, iterations, status, eerror ...
+    double* history;        // [2*max_iter]
+};
+
+struct HfIntegConsts {
+    double dl2, dl5, a2, xl4, xlp, z, pw12, xkappa;
+    int nnideal, nr;
+};
+
+// integ (libphsh.f:992-1165) with istop = 0 on entry.  Returns the verdict (ief after elsolve's node-count override,
+// :763) and, in `reach`, the last index of phi the sweep assigns.  WRITE = true also stores phi, with the |p2| > 1e10
+// rescalings recorded so that the warp can apply them in parallel afterwards.
+template <bool WRITE>
+__device__ int hf_integ(double e, const HfIntegConsts& c, const double* __restrict__ v, const double* __restrict__ xm1,
+                        const double* __restrict__ xm2, const double* __restrict__ r, const double* __restrict__ r2,
+                        double* phi, int* ev_idx, double* ev_div, int& nev, int& reach) {
+    const int nr = c.nr;
+    double t = __dsub_rn(e, v[0]);
+    const double xm0 = __dadd_rn(1.0, __dmul_rn(c.a2, t));
+    double tm = __dadd_rn(xm0, xm0);
+    double xmx = __ddiv_rn(xm1[0], xm0);
+    const double xk0 = __dsub_rn(
+        __dmul_rn(r2[0], __dadd_rn(__dsub_rn(__dmul_rn(tm, t),
+                                             __dmul_rn(xmx, __dadd_rn(__ddiv_rn(c.xkappa, r[0]), __dmul_rn(0.75, xmx)))),
+                                   __ddiv_rn(xm2[0], tm))),
+        c.xl4);
+    const double dk0 = __dadd_rn(1.0, __dmul_rn(c.dl2, xk0));
+    double p0 = dk0;
+    if (WRITE) phi[0] = __ddiv_rn(__dmul_rn(p0, sqrt(__dmul_rn(xm0, r[0]))), dk0);
+    t = __dsub_rn(e, v[1]);
+    double xm = __dadd_rn(1.0, __dmul_rn(c.a2, t));
+    tm = __dadd_rn(xm, xm);
+    xmx = __ddiv_rn(xm1[1], xm);
+    double xk2 = __dsub_rn(
+        __dmul_rn(r2[1], __dadd_rn(__dsub_rn(__dmul_rn(tm, t),
+                                             __dmul_rn(xmx, __dadd_rn(__ddiv_rn(c.xkappa, r[1]), __dmul_rn(0.75, xmx)))),
+                                   __ddiv_rn(xm2[1], tm))),
+        c.xl4);
+    double dk2 = __dadd_rn(1.0, __dmul_rn(c.dl2, xk2));
+    double p1 = __dmul_rn(
+        __dmul_rn(dk2, __dsub_rn(c.pw12, __ddiv_rn(__dmul_rn(__dsub_rn(r[1], r[0]), c.z), c.xlp))), sqrt(__ddiv_rn(xm0, xm)));
+    if (WRITE) phi[1] = __ddiv_rn(__dmul_rn(p1, sqrt(__dmul_rn(xm, r[1]))), dk2);
+    // classical turning point (:1059-1068)
+    int istop = 0;
+    for (int j = nr - 1; j >= 2; --j)
+        if (e > v[j - 1]) {
+            istop = j;
+            break;
+        }
+    reach = 2;
+    if (istop == 0) return -1;
+    int nn = 0;
+    // the two loops of the Fortran (3..istop+2 and istop+3..nr-1) differ only by the blow-up test of the second
+    const int last = max(min(istop + 2, nr), nr - 1);
+    for (int i = 3; i <= last; ++i) {
+        t = __dsub_rn(e, v[i - 1]);
+        xm = __dadd_rn(1.0, __dmul_rn(c.a2, t));
+        tm = __dadd_rn(xm, xm);
+        xmx = __ddiv_rn(xm1[i - 1], xm);
+        double p2 = __dsub_rn(__ddiv_rn(__dmul_rn(__dsub_rn(2.0, __dmul_rn(c.dl5, xk2)), p1), dk2), p0);
+        if (i > istop + 2 && __ddiv_rn(p2, p1) > 1.0) return -1;
+        xk2 = __dsub_rn(
+            __dmul_rn(r2[i - 1],
+                      __dadd_rn(__dsub_rn(__dmul_rn(tm, t), __dmul_rn(xmx, __dadd_rn(__ddiv_rn(c.xkappa, r[i - 1]),
+                                                                                   __dmul_rn(0.75, xmx)))),
+                                __ddiv_rn(xm2[i - 1], tm))),
+            c.xl4);
+        dk2 = __dadd_rn(1.0, __dmul_rn(c.dl2, xk2));
+        if (WRITE) phi[i - 1] = __ddiv_rn(__dmul_rn(p2, sqrt(__dmul_rn(xm, r[i - 1]))), dk2);
+        reach = i;
+        if (fabs(p2) > 10000000000.0) {
+            if (WRITE) {
+                if (nev < kHfMaxEvents) {
+                    ev_idx[nev] = i;
+                    ev_div[nev] = p2;
+                    ++nev;
+                } else {  // list full (never for a physical atom): divide at once like the Fortran
+                    for (int j = 1; j <= i; ++j) phi[j - 1] = __ddiv_rn(phi[j - 1], p2);
+                }
+            }
+            p0 = __ddiv_rn(p0, p2);
+            p1 = __ddiv_rn(p1, p2);
+            p2 = __ddiv_rn(p2, p2);
+        }
+        if (__dmul_rn(p2, p1) < 0.0) {
+            nn = nn + 1;
+            if (nn > c.nnideal) return 1;
+        }
+        p0 = p1;
+        p1 = p2;
+    }
+    return nn < c.nnideal ? -1 : 0;  // elsolve :763
+}
+
+// grid = number of atoms, block = 1024 threads
+__global__ void __launch_bounds__(1024, 1) hartfock_kernel(const HfProblem* __restrict__ probs) {
+    const HfProblem& P = probs[blockIdx.x];
+    const int nr = P.nr, nel = P.nel, tid = threadIdx.x, nth = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    const double* __restrict__ r = P.r;
+    const double* __restrict__ dr = P.dr;
+    const double* __restrict__ r2 = P.r2;
+    __shared__ double ev_s[kHfMaxOrb], evnew_s[kHfMaxOrb], ek_s[kHfMaxOrb], xnorm_s[kHfMaxOrb];
+    __shared__ int status_s[kHfMaxOrb];
+    __shared__ double red_s[32];
+    __shared__ double etot_s, eerror_s;
+    __shared__ int ev_idx_s[32][kHfMaxEvents];     // per warp: rescale events of a replayed sweep
+    __shared__ double ev_div_s[32][kHfMaxEvents];
+    __shared__ int nev_s[32];
+    __shared__ double stk_e_s[32][kHfMaxStack];    // per warp: sweeps of the current bisection that still own entries of phi
+    __shared__ int stk_reach_s[32][kHfMaxStack];
+
+    const double cl = 137.038;
+    const double alpha = __ddiv_rn(P.rel, cl);
+    const double aa = __dmul_rn(alpha, alpha);
+    const double a2 = __ddiv_rn(aa, 2.0);
+    const double zeff = P.z;
+    const double zaa = __dmul_rn(zeff, aa), za2 = __dmul_rn(zeff, a2);
+    const double dl = P.dl;
+    const double ratio = P.ratio, ratio1 = __dsub_rn(1.0, P.ratio);
+
+    for (int i = tid; i < nel; i += nth) ev_s[i] = 0.0;
+    for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
+        P.phe[k] = 0.0;
+        P.orb[k] = 0.0;
+    }
+    __syncthreads();
+
+    int iter = 0;
+    for (;;) {
+        // ---- setqmm (:844-931), njrc = 0: v, xm1, xm2 of every orbital ------------------------------------------
+        for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
+            const int o = static_cast<int>(k / nr), j = static_cast<int>(k % nr) + 1;
+            const double* orb = P.orb + static_cast<long>(o) * nr;
+            P.v[k] = __dadd_rn(__ddiv_rn(-zeff, r[j - 1]), orb[j - 1]);
+            if (j >= 2 && j <= nr - 1) {
+                const double dvdl = __ddiv_rn(__dsub_rn(orb[j], orb[j - 2]), __dmul_rn(2.0, dl));
+                const double ddvdrr = __ddiv_rn(
+                    __dsub_rn(__ddiv_rn(__dsub_rn(__dadd_rn(orb[j], orb[j - 2]), __dmul_rn(2.0, orb[j - 1])), __dmul_rn(dl, dl)),
+                              dvdl),
+                    r2[j - 1]);
+                P.xm1[k] = __dsub_rn(__ddiv_rn(__dmul_rn(-a2, dvdl), r[j - 1]), __ddiv_rn(za2, r2[j - 1]));
+                P.xm2[k] = __dadd_rn(__dmul_rn(-a2, ddvdrr), __ddiv_rn(__ddiv_rn(zaa, r2[j - 1]), r[j - 1]));
+            }
+        }
+        __syncthreads();
+        for (int o = tid; o < nel; o += nth) {
+            double* xm1 = P.xm1 + static_cast<long>(o) * nr;
+            double* xm2 = P.xm2 + static_cast<long>(o) * nr;
+            xm1[nr - 1] = xm1[nr - 2];
+            xm2[nr - 1] = xm2[nr - 2];
+            xm1[0] = __dsub_rn(__dadd_rn(xm1[1], __ddiv_rn(za2, r2[1])), __ddiv_rn(za2, r2[0]));
+            xm2[0] = __dadd_rn(__dsub_rn(xm2[1], __ddiv_rn(__ddiv_rn(zaa, r2[1]), r[1])), __ddiv_rn(__ddiv_rn(zaa, r2[0]), r[0]));
+        }
+        __syncthreads();
+
+        // ---- elsolve (:742-793): one warp per orbital, five bisection levels per round ---------------------------
+        for (int o = warp; o < nel; o += nwarps) {
+            const double* v = P.v + static_cast<long>(o) * nr;
+            const double* xm1 = P.xm1 + static_cast<long>(o) * nr;
+            const double* xm2 = P.xm2 + static_cast<long>(o) * nr;
+            double* phi = P.phe + static_cast<long>(o) * nr;
+            double* phi2 = P.phi2 + static_cast<long>(o) * nr;
+            const int n = P.no[o], l = P.nl[o];
+            const double xj = P.xnj[o];
+            HfIntegConsts c;
+            c.dl2 = __ddiv_rn(__dmul_rn(dl, dl), 12.0);
+            c.dl5 = __dmul_rn(10.0, c.dl2);
+            c.a2 = a2;
+            const double xl2 = __dadd_rn(0.5, static_cast<double>(l));
+            c.xl4 = __dmul_rn(xl2, xl2);
+            c.xlp = static_cast<double>(l + 1);
+            c.z = zeff;
+            c.pw12 = P.pw12[o];
+            double xkappa = -1.0;
+            if (fabs(xj) > static_cast<double>(l) + 0.25) xkappa = static_cast<double>(-l - 1);
+            if (fabs(xj) < static_cast<double>(l) - 0.25) xkappa = static_cast<double>(l);
+            c.xkappa = xkappa;
+            c.nnideal = n - l - 1;
+            c.nr = nr;
+            double el = __ddiv_rn(__dmul_rn(-P.z, P.z), static_cast<double>(n * n));
+            double eh = 0.0;
+            const double etol = 0.0000000001;
+            double e_last = 0.0;
+            int status = 0;  // 0 running, 1 converged, 2 'MIXING TOO STRONG'
+            // Every sweep of the serial bisection writes phi(1..reach) of the SAME array, so what elsolve finally holds is,
+            // index by index, the value of the LATEST sweep that got that far (the last sweeps usually stop early, in
+            // the tail).  The sweeps that still own a range are the suffix maxima of `reach` along the path: kept as a
+            // stack (reach strictly decreasing towards the top) and replayed in order once the eigenvalue is found.
+            int nstk = 0;
+            bool replay_all = false;  // stack overflow (never seen): fall back to replaying nothing but the last sweep
+            // node of this lane in the 5-level tree: depth d, index idx within the level
+            const int d_me = 31 - __clz(lane + 1), idx_me = lane + 1 - (1 << d_me);
+            while (status == 0) {
+                // the interval this lane's node would see if the bisection took the path that leads to it
+                double el_n = el, eh_n = eh;
+                bool reachable = lane < 31;
+                for (int t = 0; t < d_me && reachable; ++t) {
+                    const double et = __ddiv_rn(__dadd_rn(el_n, eh_n), 2.0);
+                    if (((idx_me >> (d_me - 1 - t)) & 1) == 0) {
+                        el_n = et;
+                        if (el_n > -0.001) reachable = false;  // the serial code returns there
+                    } else {
+                        eh_n = et;
+                    }
+                    if (!(__dsub_rn(eh_n, el_n) > etol)) reachable = false;  // ... or has converged
+                }
+                const double e_n = __ddiv_rn(__dadd_rn(el_n, eh_n), 2.0);
+                int nev_dummy = 0, reach_n = 0;
+                int ief_n = 0;
+                if (reachable)
+                    ief_n = hf_integ<false>(e_n, c, v, xm1, xm2, r, r2, nullptr, nullptr, nullptr, nev_dummy, reach_n);
+                __syncwarp();
+                // walk the tree with the actual verdicts (every lane does the same walk)
+                int d = 0, idx = 0;
+                while (d < 5) {
+                    const int src = (1 << d) - 1 + idx;
+                    const int ief = __shfl_sync(0xffffffffu, ief_n, src);
+                    const int rch = __shfl_sync(0xffffffffu, reach_n, src);
+                    const double e = __shfl_sync(0xffffffffu, e_n, src);
+                    e_last = e;
+                    while (nstk > 0 && stk_reach_s[warp][nstk - 1] <= rch) --nstk;
+                    if (nstk < kHfMaxStack) {
+                        if (lane == 0) {
+                            stk_e_s[warp][nstk] = e;
+                            stk_reach_s[warp][nstk] = rch;
+                        }
+                        ++nstk;
+                    } else {
+                        replay_all = true;
+                    }
+                    __syncwarp();
+                    if (ief != 1) {
+                        el = e;
+                        if (el > -0.001) {
+                            status = 2;
+                            break;
+                        }
+                    }
+                    if (ief != -1) eh = e;
+                    if (!(__dsub_rn(eh, el) > etol)) {
+                        status = 1;
+                        break;
+                    }
+                    idx = 2 * idx + (ief == 1 ? 1 : 0);
+                    ++d;
+                }
+            }
+            // replay the owning sweeps, oldest first; the last one is the sweep at the final energy
+            if (replay_all) {
+                nstk = 1;
+                if (lane == 0) stk_e_s[warp][0] = e_last;
+                __syncwarp();
+            }
+            for (int q = 0; q < nstk; ++q) {
+                if (lane == 0) {
+                    int nev = 0, rch = 0;
+                    hf_integ<true>(stk_e_s[warp][q], c, v, xm1, xm2, r, r2, phi, ev_idx_s[warp], ev_div_s[warp], nev, rch);
+                    nev_s[warp] = nev;
+                }
+                __syncwarp();
+                // the rescalings of that sweep: entry j was divided by every later event's p2, in order
+                const int nev = nev_s[warp];
+                if (nev > 0)
+                    for (int j = 1 + lane; j <= nr; j += 32) {
+                        double x = phi[j - 1];
+                        for (int k = 0; k < nev; ++k)
+                            if (ev_idx_s[warp][k] >= j) x = __ddiv_rn(x, ev_div_s[warp][k]);
+                        phi[j - 1] = x;
+                    }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                evnew_s[o] = e_last;
+                status_s[o] = status;
+            }
+            // entries no sweep of this bisection reached keep the previous iteration's values, as in the Fortran
+            if (status == 1) {
+                if (fabs(__dsub_rn(fabs(xj), fabs(static_cast<double>(l)))) > 0.25) {
+                    // augment (:796-841)
+                    const double cc = __dmul_rn(cl, cl);
+                    const double c2 = __dadd_rn(cc, cc);
+                    for (int j = 1 + lane; j <= nr; j += 32) {
+                        double out = 0.0;  // phi2(nr-2..nr) is never assigned by the Fortran: a fresh work array holds 0
+                        if (j >= 4 && j <= nr - 3) {
+                            if (phi[j - 1] != 0.0) {
+                                const double g0 = phi[j - 1];
+                                const double ga = __dsub_rn(phi[j], phi[j - 2]);
+                                const double gb = __ddiv_rn(__dsub_rn(phi[j + 1], phi[j - 3]), 2.0);
+                                const double gc = __ddiv_rn(__dsub_rn(phi[j + 2], phi[j - 4]), 3.0);
+                                const double gg = __ddiv_rn(
+                                    __dadd_rn(__ddiv_rn(__dadd_rn(__dsub_rn(__dmul_rn(1.5, ga), __dmul_rn(0.6, gb)),
+                                                                  __dmul_rn(0.1, gc)),
+                                                        __dmul_rn(2.0, dl)),
+                                              __dmul_rn(xkappa, g0)),
+                                    r[j - 1]);
+                                const double f0 = __ddiv_rn(__dmul_rn(cl, gg), __dadd_rn(__dsub_rn(e_last, v[j - 1]), c2));
+                                out = sqrt(__dadd_rn(__dmul_rn(g0, g0), __dmul_rn(f0, f0)));
+                                if (g0 < 0.0) out = -out;
+                            } else {
+                                out = phi[j - 1];
+                            }
+                        }
+                        phi2[j - 1] = out;
+                    }
+                    __syncwarp();
+                    if (lane < 3) phi2[lane] = __ddiv_rn(__dmul_rn(phi[lane], phi[3]), phi2[3]);
+                    __syncwarp();
+                    for (int j = lane; j < nr; j += 32) phi[j] = phi2[j];
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    double s = 0.0;
+                    for (int j = 0; j < nr; ++j) s = __dadd_rn(s, __dmul_rn(__dmul_rn(phi[j], phi[j]), dr[j]));
+                    xnorm_s[o] = sqrt(s);
+                }
+                __syncwarp();
+                const double xnorm = xnorm_s[o];
+                for (int j = lane; j < nr; j += 32) phi[j] = __ddiv_rn(phi[j], xnorm);
+                __syncwarp();
+            }
+            // kinetic energy (:416-427)
+            if (lane == 0) {
+                const double evi = e_last;
+                const double* orb = P.orb + static_cast<long>(o) * nr;
+                double ekk = 0.0;
+                int ll = 2;
+                for (int j = nr; j >= 1; --j) {
+                    const double dq = __dmul_rn(phi[j - 1], phi[j - 1]);
+                    ekk = __dadd_rn(ekk, __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dsub_rn(evi, orb[j - 1]), dr[j - 1]), dq),
+                                                             static_cast<double>(ll)),
+                                                   3.0));
+                    ll = 6 - ll;
+                }
+                ek_s[o] = ekk;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double eerror = 0.0, etot = 0.0;
+            for (int i = 0; i < nel; ++i) {
+                const double dlt = fabs(__dsub_rn(ev_s[i], evnew_s[i]));
+                if (dlt > eerror) eerror = dlt;
+                ev_s[i] = evnew_s[i];
+                etot = __dadd_rn(etot, __dmul_rn(ek_s[i], P.occ[i]));
+            }
+            eerror_s = eerror;
+            etot_s = etot;
+        }
+        // ---- getpot (:443-739) -----------------------------------------------------------------------------------
+        for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) P.orb[k] = __dmul_rn(ratio1, P.orb[k]);
+        double etot_part = 0.0;
+        const double xnum2 = __dmul_rn(P.xnum, P.xnum);
+        for (int t = tid; t < P.nterms; t += nth) {
+            const HfTerm T = P.terms[t];
+            const double* __restrict__ pi = P.phe + static_cast<long>(T.i) * nr;
+            const double* __restrict__ pj = P.phe + static_cast<long>(T.j) * nr;
+            const double* __restrict__ rpa = P.rpower + static_cast<long>(T.la) * nr;
+            const double* __restrict__ rpb = P.rpower + static_cast<long>(T.la + 1) * nr;
+            double* ci = P.contrib + (static_cast<long>(t) * 2 + 0) * nr;  // added to orb(:, i)
+            double* cj = P.contrib + (static_cast<long>(t) * 2 + 1) * nr;  // added to orb(:, j)
+            if (T.kind == 0) {
+                double xouti = 0.0, xoutj = 0.0;
+                for (int k = 0; k < nr; ++k) {
+                    const double qi0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[k], pi[k]), pi[k]), 2.0);
+                    const double qj0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[k], pj[k]), pj[k]), 2.0);
+                    const double b = rpb[k];
+                    xouti = __dadd_rn(xouti, b != 0.0 ? __ddiv_rn(qi0, b) : 0.0);
+                    xoutj = __dadd_rn(xoutj, b != 0.0 ? __ddiv_rn(qj0, b) : 0.0);
+                }
+                double qi0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[0], pi[0]), pi[0]), 2.0);
+                double qj0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[0], pj[0]), pj[0]), 2.0);
+                double qi1p = __dmul_rn(qi0, rpa[0]), qj1p = __dmul_rn(qj0, rpa[0]);
+                double qi2p = rpb[0] != 0.0 ? __ddiv_rn(qi0, rpb[0]) : 0.0, qj2p = rpb[0] != 0.0 ? __ddiv_rn(qj0, rpb[0]) : 0.0;
+                double xinti = qi1p, xintj = qj1p;
+                xouti = __dsub_rn(__dmul_rn(2.0, xouti), qi2p);
+                xoutj = __dsub_rn(__dmul_rn(2.0, xoutj), qj2p);
+                ci[0] = 0.0;
+                cj[0] = 0.0;
+                for (int k = 1; k < nr; ++k) {
+                    qi0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[k], pi[k]), pi[k]), 2.0);
+                    qj0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[k], pj[k]), pj[k]), 2.0);
+                    const double a = rpa[k], b = rpb[k];
+                    const double qi1 = __dmul_rn(qi0, a), qj1 = __dmul_rn(qj0, a);
+                    const double qi2 = b != 0.0 ? __ddiv_rn(qi0, b) : 0.0, qj2 = b != 0.0 ? __ddiv_rn(qj0, b) : 0.0;
+                    xinti = __dadd_rn(__dadd_rn(xinti, qi1), qi1p);
+                    xouti = __dsub_rn(__dsub_rn(xouti, qi2), qi2p);
+                    double vali = __dmul_rn(xouti, a);
+                    if (b != 0.0) vali = __dadd_rn(vali, __ddiv_rn(xinti, b));
+                    cj[k] = __dmul_rn(T.ri, vali);
+                    xintj = __dadd_rn(__dadd_rn(xintj, qj1), qj1p);
+                    xoutj = __dsub_rn(__dsub_rn(xoutj, qj2), qj2p);
+                    double valj = __dmul_rn(xoutj, a);
+                    if (b != 0.0) valj = __dadd_rn(valj, __ddiv_rn(xintj, b));
+                    ci[k] = __dmul_rn(T.rj, valj);
+                    etot_part = __dadd_rn(etot_part, __dmul_rn(T.rc, __dadd_rn(__dmul_rn(qi0, valj), __dmul_rn(qj0, vali))));
+                    qi1p = qi1;
+                    qj1p = qj1;
+                    qi2p = qi2;
+                    qj2p = qj2;
+                }
+            } else {
+                double xout = 0.0;
+                for (int k = 0; k < nr; ++k) {
+                    const double q0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[k], pi[k]), pj[k]), 2.0);
+                    const double b = rpb[k];
+                    xout = __dadd_rn(xout, b != 0.0 ? __ddiv_rn(q0, b) : 0.0);
+                }
+                double q0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[0], pi[0]), pj[0]), 2.0);
+                double q1p = __dmul_rn(q0, rpa[0]);
+                double q2p = rpb[0] != 0.0 ? __ddiv_rn(q0, rpb[0]) : 0.0;
+                double xint = q1p;
+                xout = __dsub_rn(__dmul_rn(2.0, xout), q2p);
+                ci[0] = 0.0;
+                cj[0] = 0.0;
+                for (int k = 1; k < nr; ++k) {
+                    q0 = __ddiv_rn(__dmul_rn(__dmul_rn(dr[k], pi[k]), pj[k]), 2.0);
+                    const double a = rpa[k], b = rpb[k];
+                    const double q1 = __dmul_rn(q0, a);
+                    const double q2 = b != 0.0 ? __ddiv_rn(q0, b) : 0.0;
+                    xint = __dadd_rn(__dadd_rn(xint, q1), q1p);
+                    xout = __dsub_rn(__dsub_rn(xout, q2), q2p);
+                    double to_i = 0.0, to_j = 0.0;
+                    if (q0 != 0.0) {
+                        double val = __dmul_rn(xout, a);
+                        if (b != 0.0) val = __dadd_rn(val, __ddiv_rn(xint, b));
+                        etot_part = __dsub_rn(etot_part, __dmul_rn(__dmul_rn(__dmul_rn(2.0, q0), T.rc), val));
+                        double xx = __ddiv_rn(pj[k], pi[k]);
+                        if (__ddiv_rn(fabs(xx), P.xnum) > 1.0)
+                            to_i = -__dmul_rn(__ddiv_rn(__dmul_rn(T.rj, xnum2), xx), val);
+                        else
+                            to_i = -__dmul_rn(__dmul_rn(T.rj, xx), val);
+                        xx = __ddiv_rn(pi[k], pj[k]);
+                        if (__ddiv_rn(fabs(xx), P.xnum) > 1.0)
+                            to_j = -__dmul_rn(__ddiv_rn(__dmul_rn(T.ri, xnum2), xx), val);
+                        else
+                            to_j = -__dmul_rn(__dmul_rn(T.ri, xx), val);
+                    }
+                    ci[k] = to_i;
+                    cj[k] = to_j;
+                    q1p = q1;
+                    q2p = q2;
+                }
+            }
+        }
+        __syncthreads();
+        // add the contributions in the order of the reference's pair loops: one thread per (orbital, r)
+        for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
+            const int o = static_cast<int>(k / nr), kk = static_cast<int>(k % nr);
+            if (kk == 0) continue;  // the k loops of getpot start at 2
+            double x = P.orb[k];
+            for (int u = P.upd_off[o]; u < P.upd_off[o + 1]; ++u) x = __dadd_rn(x, P.contrib[static_cast<long>(P.upd[u]) * nr + kk]);
+            P.orb[k] = x;
+        }
+        // total energy (information only): per-thread partial sums, then in thread order
+        {
+            double s = etot_part;
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+            if (lane == 0) red_s[warp] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double s = etot_s;
+            for (int w = 0; w < nwarps; ++w) s += red_s[w];
+            etot_s = s;
+        }
+        __syncthreads();
+        // local exchange / correlation (:617-660) -- alfa != 0 only
+        if (fabs(P.alfa) >= 0.001) {
+            double fx, fc;
+            if (P.alfa > 0.0) {
+                fx = 1.0;
+                fc = 1.0;
+            } else {
+                fx = 1.5 * fabs(P.alfa);
+                fc = 0.0;
+            }
+            double epart = 0.0;
+            for (int i = tid; i < nr; i += nth) {
+                double xn = 0.0;
+                for (int j = 0; j < nel; ++j) {
+                    const double ph = P.phe[static_cast<long>(j) * nr + i];
+                    xn = __dadd_rn(xn, __dmul_rn(__dmul_rn(ph, ph), P.occ[j]));
+                }
+                const double rh1 = __ddiv_rn(xn, 2.0);
+                // exchcorr (:1923-2067) with nst = 2, rh1 = rh2
+                const double trd = 1.0 / 3.0, ft = 4.0 / 3.0, pi_ = 3.14159265358979, fp = 4.0 * pi_;
+                const double xn1 = rh1 / (r2[i] * fp);
+                const double xnn = xn1 + xn1;
+                double ex = 0.0, ec = 0.0, ux1 = 0.0, uc1 = 0.0;
+                if (!(xnn < 0.00000001)) {
+                    const double rs = pow(3.0 / (fp * xnn), trd);
+                    double fe1 = 1.0, fu1 = 1.0, ex1 = 0.0;
+                    if (xn1 != 0.0) {
+                        const double beta = 0.028433756 * pow(xn1, trd);
+                        const double b2 = beta * beta;
+                        const double eta = sqrt(1.0 + b2);
+                        const double xl = log(beta + eta);
+                        const double tq = (beta * eta - xl) / b2;
+                        fe1 = 1.0 - 1.5 * (tq * tq);
+                        fu1 = -0.5 + 1.5 * xl / beta / eta;
+                        ex1 = -0.930525546 * pow(xn1, trd);
+                        ux1 = 4.0 * ex1 / 3.0;
+                    }
+                    double ecu, ucu;
+                    if (rs >= 1.0) {
+                        const double rootr = sqrt(rs);
+                        const double denom = (1.0 + 1.0529 * rootr + 0.3334 * rs);
+                        ecu = -0.1423 / denom;
+                        ucu = ecu * (1.0 + 7.0 / 6.0 * 1.0529 * rootr + ft * 0.3334 * rs) / denom;
+                    } else {
+                        const double xlr = log(rs), rlr = rs * xlr;
+                        ecu = 0.0311 * xlr + -0.048 + 0.002 * rlr + -0.0116 * rs;
+                        ucu = 0.0311 * xlr + (-0.048 - 0.0311 / 3.0) + 2.0 / 3.0 * 0.002 * rlr + (2.0 * -0.0116 - 0.002) * rs / 3.0;
+                    }
+                    if (P.rel == 0.0) {
+                        fe1 = 1.0;
+                        fu1 = 1.0;
+                    }
+                    // zeta = 0: f = 0 and dfdz = 0, so ec = ecu, uc1 = ucu
+                    ec = ecu;
+                    uc1 = ucu;
+                    ex = (xn1 * fe1 * ex1 + xn1 * fe1 * ex1) / xnn;
+                    ux1 = fu1 * ux1;
+                }
+                const double exc = fx * ex + fc * ec;
+                const double uxc = fx * ux1 + fc * uc1;
+                epart += dr[i] * xn * exc;
+                for (int j = 0; j < nel; ++j) {
+                    double* orb = P.orb + static_cast<long>(j) * nr;
+                    orb[i] = __dadd_rn(orb[i], __dmul_rn(uxc, ratio));
+                }
+            }
+            for (int off = 16; off > 0; off >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, off);
+            __syncthreads();
+            if (lane == 0) red_s[warp] = epart;
+            __syncthreads();
+            if (tid == 0) {
+                double s = etot_s;
+                for (int w = 0; w < nwarps; ++w) s += red_s[w];
+                etot_s = s;
+            }
+        }
+        __syncthreads();
+        // shell averaging (:662-736), iuflag = 1: same n, l, spin; 2: same n, l
+        if (P.iuflag != 0) {
+            for (int i = tid; i < nr; i += nth) {
+                int jj = 0;
+                for (;;) {
+                    int ii = jj;
+                    while (ii != nel - 1) {
+                        bool cond = false;
+                        if (P.no[jj] == P.no[ii + 1] && P.nl[jj] == P.nl[ii + 1] && P.iuflag == 2) cond = true;
+                        if (P.no[jj] == P.no[ii + 1] && P.nl[jj] == P.nl[ii + 1] && P.is[jj] == P.is[ii + 1] && P.iuflag == 1)
+                            cond = true;
+                        if (!cond) break;
+                        ++ii;
+                    }
+                    double orba = 0.0, div = 0.0;
+                    for (int k = jj; k <= ii; ++k) {
+                        div = __dadd_rn(div, P.occ[k]);
+                        orba = __dadd_rn(orba, __dmul_rn(P.orb[static_cast<long>(k) * nr + i], P.occ[k]));
+                    }
+                    if (div != 0.0) {
+                        orba = __ddiv_rn(orba, div);
+                        for (int k = jj; k <= ii; ++k) P.orb[static_cast<long>(k) * nr + i] = orba;
+                    }
+                    if (ii == nel - 1) break;
+                    jj = ii + 1;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- convergence (abinitio :338-349) -----------------------------------------------------------------------
+        const double eerr = __ddiv_rn(__dmul_rn(eerror_s, ratio1), ratio);
+        if (tid == 0 && iter < P.max_iter) {
+            P.history[2 * iter] = eerr;
+            P.history[2 * iter + 1] = etot_s;
+        }
+        ++iter;
+        if (!(eerr > P.etol) || iter >= P.max_iter) break;
+        __syncthreads();
+    }
+    __syncthreads();
+    // charge density of hfdisk (:1889-1896) and the bookkeeping
+    for (int i = tid; i < nr; i += nth) {
+        double s = 0.0;
+        for (int ii = 0; ii < nel; ++ii) {
+            const double ph = P.phe[static_cast<long>(ii) * nr + i];
+            s = __dadd_rn(s, __dmul_rn(P.occ[ii], __dmul_rn(ph, ph)));
+        }
+        P.rho[i] = s;
+    }
+    for (int i = tid; i < nel; i += nth) {
+        P.ev[i] = ev_s[i];
+        P.ek[i] = ek_s[i];
+    }
+    if (tid == 0) {
+        int mixing = 0;
+        for (int i = 0; i < nel; ++i) mixing |= (status_s[i] == 2);
+        P.info[0] = etot_s;
+        P.info[1] = static_cast<double>(iter);
+        P.info[2] = static_cast<double>(mixing);
+        P.info[3] = __ddiv_rn(__dmul_rn(eerror_s, ratio1), ratio);
+    }
+}
+
+}  // namespace phsh

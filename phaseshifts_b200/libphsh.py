@@ -15,8 +15,11 @@ The producer of the path's input is here too:
     cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file) -> float
                                                  libphsh.f:2070  (called from model.py:935)
 
-The atomic step (``hartfock``) is NOT part of this package: if the real extension is importable it is delegated to
-it, otherwise it raises.  ``hb`` (a closed-form helper the f2py module also exports) is evaluated directly.
+and so is the atomic step in front of it (row 3):
+
+    hartfock(input_file)                         libphsh.f:60    (called from atorb.py:1201)
+
+``hb`` (a closed-form helper the f2py module also exports) is evaluated directly.
 
 Environment switches (read at call time):
   PHSH_B200_DEVICE=<n>        CUDA device index (default 0)
@@ -27,6 +30,7 @@ Environment switches (read at call time):
   PHSH_B200_MAX_ENERGIES=<n>  energy cap of PHSH_REL (reference: 250, libphsh.f:4642); 0 lifts it
   PHSH_B200_MAX_JRI=<n>       radial-point cap (reference: 340, libphsh.f:4609); 0 lifts it
   PHSH_B200_CAVPOT_DELEGATE=1 hand ``cavpot`` to the real f2py extension (when importable) instead of the GPU
+  PHSH_B200_HARTFOCK_DELEGATE=1 the same for ``hartfock``
   PHSH_B200_CAV_ORIGINAL_HEADER=1  keep PHSH_CAV's own phasout header (NL instead of lmax), which the
                               reference's Conphas cannot parse
 """
@@ -80,17 +84,6 @@ def _s(x):
     return str(x).strip()
 
 
-def _upstream(name):
-    def call(*args, **kwargs):
-        if _delegate is not None and hasattr(_delegate, name):
-            return getattr(_delegate, name)(*args, **kwargs)
-        raise NotImplementedError(
-            "libphsh.%s (the atomic charge-density step) is not provided by phaseshifts_b200; build the reference's "
-            "Fortran extension or supply existing at_<element>.i files for this step" % name)
-    call.__name__ = name
-    return call
-
-
 def cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, output_file, info_file):
     """Muffin-tin potential of a cluster (``libphsh.f:2070-2557``): reads ``cluster.i`` + ``atomic.i``, writes
     ``mufftin.d`` in the cluster file's NFORM, the muffin-tin zero to ``output_file`` (bulk runs) and a summary to
@@ -102,7 +95,12 @@ def cavpot(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, outpu
                            asbuilt=_flag("PHSH_B200_ASBUILT"))
 
 
-hartfock = _upstream("hartfock")  # libphsh.f:60    atomic charge densities (step 0)
+def hartfock(input_file):
+    """Atomic charge densities (``libphsh.f:60-2068``): runs the command stream of an ``atorb`` input file and writes the
+    ``at_<El>.i`` file(s) its ``w`` commands name, relative to the current directory like the Fortran."""
+    if _flag("PHSH_B200_HARTFOCK_DELEGATE") and _delegate is not None and hasattr(_delegate, "hartfock"):
+        return _delegate.hartfock(input_file)
+    api.hartfock_file(_s(input_file), asbuilt=_flag("PHSH_B200_ASBUILT"), device=_int("PHSH_B200_DEVICE", 0))
 
 
 def hb(x, factor):

@@ -126,8 +126,11 @@ def test_standin_module_surface(monkeypatch):
     for fn in ("phsh_rel", "phsh_cav", "phsh_wil"):
         assert len(inspect.signature(getattr(libphsh, fn)).parameters) == 4
     assert len(inspect.signature(libphsh.cavpot).parameters) == 7   # libphsh.f:2070-2071
-    with pytest.raises(NotImplementedError):
-        libphsh.hartfock("atorb_Re")
+    assert len(inspect.signature(libphsh.hartfock).parameters) == 1  # libphsh.f:60
+    seen_hf = {}
+    monkeypatch.setattr(api, "hartfock_file", lambda *a, **k: seen_hf.update(a=a, k=k))
+    assert libphsh.hartfock(b"atorb_Re  ") is None
+    assert seen_hf["a"] == ("atorb_Re",) and seen_hf["k"] == {"asbuilt": False, "device": 0}
     assert libphsh.hb(4.0, 1.0) == 0.0 and abs(libphsh.hb(1.0, 1.0) - 0.01) < 3e-7 and libphsh.hb(0.0, 2.0) == 1.0
     seen = {}
     monkeypatch.setattr(api, "cavpot_file", lambda *a, **k: seen.update(cav=a, cavkw=k) or -1.5)

@@ -110,3 +110,35 @@ def test_cli_on_device_with_energy_range(wired):
             n = int(open(work / f).readline().split()[0])
             _, got = _phs_rows(str(work / f), n)
             assert got.shape == (n, 11) and np.isfinite(got).all()
+
+
+def test_cold_start_cluster_files_only_hartfock_cavpot_phsh_rel_on_device(wired, tmp_path):
+    """Nothing pre-placed: the unmodified Wrapper finds no at_Re.i, generates the atorb input itself (atorb.py gen_input) and
+    calls `libphsh.hartfock` -> hartfock_kernel, then `libphsh.cavpot` -> cavpot_kernel, `libphsh.phsh_rel` ->
+    rel_integrate_kernel and its own Conphas.  The generated input is not the fixture's atorb_Re (5d occupations 2 + 3
+    instead of 1.875 + 3.125, another orbital order), so the at_Re.i written on the way is checked byte for byte against
+    the CPU oracle run on the very same generated input, and the .phs files against the golden leedph at the accuracy
+    that different 5d occupations leave."""
+    import phaseshifts.backends as B
+    from oracle import oracle as orc
+    from oracle import hartfock_io as hio
+    orc.build()
+    _, work = wired
+    assert not os.path.exists(work / "at_Re.i")
+    files = B.get_backend("b200").autogen_from_input(os.path.join(RE, "cluster_Re_bulk.i"),
+                                                     os.path.join(RE, "cluster_Re_bulk.i"), tmp_dir=str(work), lmax=10,
+                                                     format="cleed")
+    assert len(files) == 2
+    found = {f: os.path.join(dp, f) for dp, _, fs in os.walk(str(tmp_path)) for f in fs}
+    assert "at_Re.i" in found, "hartfock did not write at_Re.i"
+    inputs = [v for k, v in found.items() if k.startswith("atorb") and "Re" in k]
+    assert inputs, sorted(found)
+    chk = tmp_path / "oracle_out"
+    chk.mkdir()
+    hio.hartfock(inputs[0], cwd=str(chk))
+    assert open(found["at_Re.i"]).read() == open(chk / "at_Re.i").read()
+    gold = _leedph()
+    for f in files:
+        head, rows = _phs_rows(f)
+        assert head.startswith("57 10 neng lmax") and np.isfinite(rows).all()
+        assert np.abs(rows - gold).max() <= 2e-2
