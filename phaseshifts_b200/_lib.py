@@ -91,6 +91,7 @@ _SIGNATURES = {
     "phsh_b200_conphas_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int,
                                           C.POINTER(ConphasOpts)]),
     "phsh_b200_cavpot_batch_host": (C.c_int, [C.POINTER(CavpotBatch), C.POINTER(CavpotResult), C.c_int, C.c_int]),
+    "phsh_b200_cavpot_validate": (C.c_int, [C.POINTER(CavpotBatch)]),
     "phsh_b200_cavpot_batch_device": (C.c_int, [C.POINTER(CavpotBatch), C.POINTER(CavpotResult), C.c_int, C.c_void_p]),
     "phsh_b200_cavpot_rela_density": (C.c_int, [C.c_double, C.c_double, C.c_int, _dp, C.c_int, _dp, C.POINTER(C.c_int),
                                                 C.c_int]),

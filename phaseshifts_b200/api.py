@@ -127,6 +127,11 @@ def phsh_rel_batch(pot, jri, energies_ryd, lmax, *, energies_l0=None, xs=XS_DEFA
         e_stride = 0 if e_l.dim() == 1 else NE
         if e_l.dim() == 2 and e_l.shape[0] != P:
             raise ValueError("per-potential energies must be [P, NE]")
+        if e_l0.shape != e_l.shape:
+            raise ValueError("energies_l0 %s must have the shape of energies_ryd %s" % (tuple(e_l0.shape), tuple(e_l.shape)))
+        if out is not None and (not isinstance(out, torch.Tensor) or out.dtype != torch.float64 or out.device != dev or
+                                tuple(out.shape) != (P, NE, L1) or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous float64 [%d, %d, %d] tensor on %s" % (P, NE, L1, dev))
         delta = out if out is not None else torch.empty((P, NE, L1), dtype=torch.float64, device=dev)
         kap = torch.empty((P, L1, NE, 2), dtype=torch.float64, device=dev) if per_kappa else None
         cnt = torch.zeros(4, dtype=torch.int64, device=dev) if counters else None
@@ -152,6 +157,13 @@ def phsh_rel_batch(pot, jri, energies_ryd, lmax, *, energies_l0=None, xs=XS_DEFA
     e_l0 = e_l if energies_l0 is None else _np64(energies_l0)
     NE = e_l.shape[-1]
     e_stride = 0 if e_l.ndim == 1 else NE
+    if e_l.ndim not in (1, 2) or (e_l.ndim == 2 and e_l.shape[0] != P):
+        raise ValueError("energies_ryd must be [NE] or [P, NE]")
+    if e_l0.shape != e_l.shape:
+        raise ValueError("energies_l0 %s must have the shape of energies_ryd %s" % (e_l0.shape, e_l.shape))
+    if out is not None and (not isinstance(out, np.ndarray) or out.dtype != np.float64 or out.shape != (P, NE, L1) or
+                            not out.flags["C_CONTIGUOUS"]):
+        raise ValueError("out must be a C-contiguous float64 array of shape (%d, %d, %d)" % (P, NE, L1))
     delta = out if out is not None else np.empty((P, NE, L1))
     kap = np.empty((P, L1, NE, 2)) if per_kappa else None
     cnt = np.zeros(4, dtype=np.uint64)
@@ -220,8 +232,12 @@ def phsh_cav_batch(V, RX, ntab, rmt, e_ryd, NL=12, *, unwrap=False, asbuilt=Fals
     if _is_cuda_tensor(V):
         import torch
         dev = V.device
+        if V.dtype != torch.float64 or V.dim() != 2:
+            raise ValueError("V must be a float64 [P, S] tensor")
         V = V.contiguous()
         RX = torch.as_tensor(RX, dtype=torch.float64, device=dev).contiguous()
+        if RX.shape != V.shape:
+            raise ValueError("RX must have the shape of V")
         P, S = V.shape
         if S % 2:
             V = torch.nn.functional.pad(V, (0, 1)).contiguous()
@@ -258,8 +274,12 @@ def phsh_wil_batch(rs, zs, nrows, Z, RT, e, NL=9, NR=101, *, unwrap=False, devic
     if _is_cuda_tensor(rs):
         import torch
         dev = rs.device
+        if rs.dtype != torch.float64 or rs.dim() != 2:
+            raise ValueError("rs must be a float64 [P, S] tensor")
         rs = rs.contiguous()
         zs = torch.as_tensor(zs, dtype=torch.float64, device=dev).contiguous()
+        if zs.shape != rs.shape:
+            raise ValueError("zs must have the shape of rs")
         P, S = rs.shape
         if S % 2:
             rs = torch.nn.functional.pad(rs, (0, 1)).contiguous()
@@ -484,6 +504,12 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=
 
 def _cavpot_batch_device(keep, S, T, A, n_dens, device, flags=0):
     import torch
+    # the kernel indexes shared and global tables with these values: validate the host copy before uploading it
+    hb = _lib.CavpotBatch()
+    hb.n_struct, hb.n_types, hb.n_atoms, hb.n_dens = S, T, A, n_dens
+    for k, v in keep.items():
+        setattr(hb, k, v.ctypes.data)
+    _lib.check(_lib.load().phsh_b200_cavpot_validate(C.byref(hb)))
     dev = torch.device("cuda", device)
     d = {k: torch.from_numpy(v).to(dev) for k, v in keep.items()}
     to, ao = keep["type_off"], keep["atom_off"]

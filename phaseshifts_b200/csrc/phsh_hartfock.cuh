@@ -17,7 +17,7 @@
 // Everything order-dependent keeps the reference's order, every operation is the IEEE double operation of the Fortran
 // statement (file compiled with -fmad=false, __ddiv_rn, correctly rounded sqrt), and every transcendental of the
 // Hartree-Fock path (the log grid, r**k, the power-law start of integ) is tabulated on the host with libm: the
-// eigenvalues, orbitals and charge density are bit-identical to the CPU restatement (oracle/hartfock_oracle.hpp).
+// eigenvalues, orbitals and charge density are bit-identical to the CPU restatement the tests check against.
 // Exceptions: the total energy (information only, never fed back) is summed per term and then over terms; the local
 // exchange-correlation mode (alfa != 0: pow/log of exchcorr on the device) agrees to rounding, not bit for bit.
 // Bound: latency of dependent FP64 divisions (a serial recurrence per lane) -- nothing here approaches a roofline, the
