@@ -88,6 +88,7 @@ _SIGNATURES = {
     "phsh_b200_cav_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FileOpts)]),
     "phsh_b200_wil_file": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(FileOpts)]),
     "phsh_b200_split_phasout": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int]),
+    "phsh_b200_load_phase_file": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), _dp, C.c_long, C.POINTER(C.c_long)]),
     "phsh_b200_conphas_files": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int,
                                           C.POINTER(ConphasOpts)]),
     "phsh_b200_cavpot_batch_host": (C.c_int, [C.POINTER(CavpotBatch), C.POINTER(CavpotResult), C.c_int, C.c_int]),

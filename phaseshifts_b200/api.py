@@ -181,7 +181,9 @@ def phsh_rel_batch(pot, jri, energies_ryd, lmax, *, energies_l0=None, xs=XS_DEFA
 def _counter_dict(c):
     calls, steps, evals = int(c[0]), int(c[1]), int(c[2])
     # as-written FP64 operation count: 5 RK steps x 64 + 10 per call, 23 per Milne step, 28 per corrector evaluation
-    return dict(calls=calls, milne_steps=steps, corr_evals=evals, flops=330.0 * calls + 23.0 * steps + 28.0 * evals)
+    # c[3]: lanes that rejected an out-of-range jri on the device (their phases are NaN) -- the device-side error flag
+    return dict(calls=calls, milne_steps=steps, corr_evals=evals, flops=330.0 * calls + 23.0 * steps + 28.0 * evals,
+                rejected_lanes=int(c[3]))
 
 
 def conphas(phas, lmax=None, device=0):

@@ -56,16 +56,24 @@ class Conphas(object):
         else:
             self.format = None
 
-    # ---- parsing (conphas.py:171-202); kept in Python because it returns Python objects
+    # ---- parsing (conphas.py:171-202): done by the C++ file layer, handed back as the reference's tuple
     def load_data(self, filename):
-        with open(filename, "r") as f:
-            f.readline()
-            (initial_energy, energy_step, n_phases, lmf) = [
-                t(s) for (t, s) in zip((float, float, int, int), f.readline().replace("-", " -").split())
-            ]
-            data_lines = [line.replace("-", " -").replace("\n", "") for line in f.readlines()]
-            data = [float(number) for number in "".join(data_lines).split()]
-        return (initial_energy, energy_step, n_phases, lmf, data)
+        """``(initial_energy, energy_step, n_phases, lmf, data)`` of one section file, ``data`` a flat list of floats."""
+        import numpy as np
+        lib = _lib.load()
+        head = (C.c_double * 4)()
+        n = C.c_long(0)
+        path = str(filename).encode()
+        rc = lib.phsh_b200_load_phase_file(path, head, None, 0, C.byref(n))
+        buf = np.empty(max(n.value, 1))
+        if rc == 0:
+            rc = lib.phsh_b200_load_phase_file(path, head, buf.ctypes.data, n.value, C.byref(n))
+        if rc != 0:
+            msg = lib.phsh_b200_last_error().decode("utf-8", "replace")
+            if "cannot read" in msg:
+                raise IOError(msg)
+            raise ValueError(msg)
+        return (head[0], head[1], int(head[2]), int(head[3]), buf[: n.value].tolist())
 
     @staticmethod
     def split_phasout(filename, output_filenames=None):
@@ -90,17 +98,24 @@ class Conphas(object):
         return [s for s in buf.value.decode().split("\n") if s][:rc]
 
     def _resolve_v0_params(self):
-        params = getattr(self, "v0_params", None)
-        if params is None:
+        """The four Rundgren inner-potential coefficients of the ViPErLEED header, or None for the library's defaults
+        (``-10.17, -0.08, -74.19, 19.18``, conphas.py:321); anything that is not four numbers is a ValueError."""
+        given = getattr(self, "v0_params", None)
+        if given is None:
             return None
-        if not isinstance(params, (list, tuple)) or len(params) < 4:
-            raise ValueError("Invalid v0_params configuration: expected a list or tuple with at least 4 numeric "
-                             "elements, got {!r}".format(params))
-        try:
-            return tuple(float(v) for v in params[:4])
-        except (TypeError, ValueError) as exc:
-            raise ValueError("Invalid v0_params configuration: all first four elements must be numeric, "
-                             "got {!r}".format(params)) from exc
+        ok = isinstance(given, (list, tuple)) and len(given) >= 4
+        coeffs = []
+        if ok:
+            for item in given[:4]:
+                try:
+                    coeffs.append(float(item))
+                except (TypeError, ValueError):
+                    ok = False
+                    break
+        if not ok:
+            raise ValueError("v0_params must be a list or tuple whose first four entries are numbers (c0..c3 of the "
+                             "Rundgren inner potential), not %r" % (given,))
+        return tuple(coeffs)
 
     def calculate(self):
         """Continuous phase shifts from the input section(s) -> ``dataph_<name>.d`` + the formatted output file."""

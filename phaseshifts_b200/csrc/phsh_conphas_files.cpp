@@ -184,6 +184,65 @@ static int split_phasout_impl(const char* phasout, const char* const* names, int
     return static_cast<int>(idx.size());
 }
 
+// Conphas.load_data (conphas.py:171-202): the title line is skipped, the second line holds initial energy, step,
+// n_phases and lmf, and everything after it is one stream of numbers in which a '-' also starts a new number.
+static int parse_phase_file(const char* path, double* e0, double* de, int* n_phases, int* lmf, std::vector<double>* data) {
+    std::vector<std::string> lines;
+    if (!read_all_lines(path, &lines) || lines.size() < 2) {
+        set_error("cannot read phase shift file '%s'", path);
+        return PHSH_B200_EIO;
+    }
+    const std::vector<std::string> h = split_ws(dash_spaced(lines[1]));
+    double dn, dl;
+    if (h.size() < 4 || !to_double(h[0], e0) || !to_double(h[1], de) || !to_double(h[2], &dn) || !to_double(h[3], &dl) ||
+        h[2].find_first_not_of("+-0123456789") != std::string::npos ||
+        h[3].find_first_not_of("+-0123456789") != std::string::npos) {
+        set_error("'%s': bad header line (initial energy, step, n_phases, lmf)", path);
+        return PHSH_B200_EIO;
+    }
+    if (!(dn >= -2.0e9 && dn <= 2.0e9) || !(dl >= -1.0 && dl <= 1.0e4)) {
+        set_error("'%s': header values out of range (n_phases=%g, lmf=%g)", path, dn, dl);
+        return PHSH_B200_EIO;
+    }
+    *n_phases = static_cast<int>(dn);
+    *lmf = static_cast<int>(dl);
+    std::string joined;  // "".join(line.replace("-", " -").replace("\n", "")) -- no separator between lines
+    for (size_t k = 2; k < lines.size(); ++k) {
+        const std::string t = dash_spaced(lines[k]);
+        for (char c : t)
+            if (c != '\n') joined.push_back(c);
+    }
+    data->clear();
+    for (const std::string& tok : split_ws(joined)) {
+        double v;
+        if (!to_double(tok, &v)) {
+            set_error("'%s': could not convert string to float: '%s'", path, tok.c_str());
+            return PHSH_B200_EIO;
+        }
+        data->push_back(v);
+    }
+    return 0;
+}
+
+static int load_phase_file_impl(const char* path, double* header, double* data, long data_cap, long* n_data) {
+    if (!path || !header || !n_data || data_cap < 0 || (data_cap > 0 && !data)) {
+        set_error("bad arguments");
+        return PHSH_B200_EINVAL;
+    }
+    double e0 = 0, de = 0;
+    int n_phases = 0, lmf = 0;
+    std::vector<double> v;
+    const int rc = parse_phase_file(path, &e0, &de, &n_phases, &lmf, &v);
+    if (rc) return rc;
+    header[0] = e0;
+    header[1] = de;
+    header[2] = n_phases;
+    header[3] = lmf;
+    *n_data = static_cast<long>(v.size());
+    for (long k = 0; k < data_cap && k < *n_data; ++k) data[k] = v[k];
+    return 0;
+}
+
 static int conphas_files_impl(const char* const* inputs, int n_inputs, const char* output_file, const char* format,
                               int lmax, const phsh_b200_conphas_opts* opts) {
     if (!inputs || n_inputs < 0 || !output_file || lmax < 0) {
@@ -198,42 +257,12 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
     std::vector<double> energy;
     int neng = 0, n_phases = 0;
     for (int i = 0; i < n_inputs; ++i) {
-        std::vector<std::string> lines;
-        if (!read_all_lines(inputs[i], &lines) || lines.size() < 2) {
-            set_error("cannot read phase shift file '%s'", inputs[i]);
-            return PHSH_B200_EIO;
-        }
-        const std::vector<std::string> h = split_ws(dash_spaced(lines[1]));
-        double e0, de, dn, dl;
-        if (h.size() < 4 || !to_double(h[0], &e0) || !to_double(h[1], &de) || !to_double(h[2], &dn) ||
-            !to_double(h[3], &dl) || h[2].find_first_not_of("+-0123456789") != std::string::npos ||
-            h[3].find_first_not_of("+-0123456789") != std::string::npos) {
-            set_error("'%s': bad header line (initial energy, step, n_phases, lmf)", inputs[i]);
-            return PHSH_B200_EIO;
-        }
-        if (!(dn >= -2.0e9 && dn <= 2.0e9) || !(dl >= -1.0 && dl <= 1.0e4)) {
-            set_error("'%s': header values out of range (n_phases=%g, lmf=%g)", inputs[i], dn, dl);
-            return PHSH_B200_EIO;
-        }
         Section& S = secs[i];
-        S.n_phases = static_cast<int>(dn);
-        S.lmf = static_cast<int>(dl);
-        std::string joined;  // "".join(line.replace("-", " -").replace("\n", "")) -- no separator between lines
-        for (size_t k = 2; k < lines.size(); ++k) {
-            std::string t = dash_spaced(lines[k]);
-            std::string u;
-            for (char c : t)
-                if (c != '\n') u.push_back(c);
-            joined += u;
-        }
         std::vector<double> data;
-        for (const std::string& tok : split_ws(joined)) {
-            double v;
-            if (!to_double(tok, &v)) {
-                set_error("'%s': could not convert string to float: '%s'", inputs[i], tok.c_str());
-                return PHSH_B200_EIO;
-            }
-            data.push_back(v);
+        {
+            double e0, de;
+            const int prc = parse_phase_file(inputs[i], &e0, &de, &S.n_phases, &S.lmf, &data);
+            if (prc) return prc;
         }
         n_phases = S.n_phases;
         if (n_phases > 250) n_phases = 250;  // conphas.py:412-413
@@ -424,6 +453,9 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
 int phsh_b200_split_phasout(const char* phasout, const char* const* names, int n_names, char* written,
                             int written_cap) {
     PHSH_GUARDED(split_phasout_impl(phasout, names, n_names, written, written_cap))
+}
+int phsh_b200_load_phase_file(const char* path, double* header, double* data, long data_cap, long* n_data) {
+    PHSH_GUARDED(load_phase_file_impl(path, header, data, data_cap, n_data))
 }
 int phsh_b200_conphas_files(const char* const* inputs, int n_inputs, const char* output_file, const char* format,
                             int lmax, const phsh_b200_conphas_opts* opts) {

@@ -463,15 +463,18 @@ __global__ void __launch_bounds__(128, MINB)
     }
     if (counters != nullptr) {
         __syncwarp();
+        unsigned bad = (active && !valid) ? 1u : 0u;  // lanes whose jri was rejected (their phases are NaN): the error flag
         for (int o = 16; o > 0; o >>= 1) {
             steps += __shfl_down_sync(0xffffffffu, steps, o);
             evals += __shfl_down_sync(0xffffffffu, evals, o);
             calls += __shfl_down_sync(0xffffffffu, calls, o);
+            bad += __shfl_down_sync(0xffffffffu, bad, o);
         }
         if ((threadIdx.x & 31) == 0) {
             atomicAdd(&counters[0], static_cast<unsigned long long>(calls));
             atomicAdd(&counters[1], static_cast<unsigned long long>(steps));
             atomicAdd(&counters[2], static_cast<unsigned long long>(evals));
+            if (bad) atomicAdd(&counters[3], static_cast<unsigned long long>(bad));
         }
     }
 }

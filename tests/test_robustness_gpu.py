@@ -100,6 +100,12 @@ def test_bad_inputs_on_device_give_nan_not_faults(oracle):
     ref = oracle.rel_batch(w["pot"][[0, 3]], [321, 326], g["e_l0"], g["e_l"], lsm=3)["jf"]
     ref = np.stack([oracle.conphas(x) for x in ref])
     assert np.abs(d[[0, 3]] - ref).max() <= TOL
+    # the device-side error flag: the counters count every lane that rejected its jri (2 potentials x 40 energies,
+    # once per l-group CTA), and none on a clean batch
+    _, cnt = api.phsh_rel_batch(pot, jri, g["e_l"], 3, energies_l0=g["e_l0"], counters=True)
+    assert cnt["rejected_lanes"] >= 2 * 40 and cnt["rejected_lanes"] % (2 * 40) == 0
+    _, cnt = api.phsh_rel_batch(pot[[0, 3]], jri[[0, 3]], g["e_l"], 3, energies_l0=g["e_l0"], counters=True)
+    assert cnt["rejected_lanes"] == 0
     with pytest.raises(PhshB200Error):  # the host entry point can check, and does
         api.phsh_rel_batch(w["pot"], [321, 6, 999, 326], g["e_l"], 3)
     # E <= 0: SBFIT's sqrt(E) is NaN / 0, every comparison on NaN is false and the reference falls through to its
