@@ -67,6 +67,8 @@ _SIGNATURES = {
     "phsh_b200_version": (C.c_char_p, []),
     "phsh_b200_device_count": (C.c_int, []),
     "phsh_b200_trim": (C.c_int, [C.c_int]),
+    "phsh_b200_guard_violations": (C.c_long, [C.POINTER(C.c_long)]),
+    "phsh_b200_guard_selftest": (C.c_int, [C.c_int]),
     "phsh_b200_rel_batch_device": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_long, C.c_int,
                                              C.POINTER(RelOpts), _dp, _dp, _dp, C.c_void_p]),
     "phsh_b200_rel_integrate_device": (C.c_int, [_dp, C.c_long, _dp, C.c_int, _dp, _dp, C.c_long, C.c_int,

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstring>
 #include <limits>
+#include <atomic>
 #include <mutex>
 #include <cstdint>
 #include <vector>
@@ -110,6 +111,16 @@ int select_device(int device) {
     return check_current_device();
 }
 
+static bool guard_enabled() {
+    static const bool on = [] {
+        const char* g = getenv("PHSH_B200_GUARD");
+        return g && g[0] && g[0] != '0';
+    }();
+    return on;
+}
+static std::atomic<long> g_guard_violations{0};
+static std::atomic<long> g_guard_checked{0};
+
 int DeviceBuf::alloc(size_t bytes, cudaStream_t stream) {
     s = stream;
     int dev = 0;
@@ -117,8 +128,47 @@ int DeviceBuf::alloc(size_t bytes, cudaStream_t stream) {
     DeviceCtx* c = nullptr;
     int rc = device_ctx(dev, &c);
     if (rc) return rc;
-    PHSH_CUDA(cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, c->pool, stream));
+    if (!bytes) bytes = 16;
+    if (!guard_enabled()) {
+        PHSH_CUDA(cudaMallocFromPoolAsync(&p, bytes, c->pool, stream));
+        return 0;
+    }
+    const size_t body = (bytes + 255) & ~static_cast<size_t>(255);
+    void* base = nullptr;
+    PHSH_CUDA(cudaMallocFromPoolAsync(&base, body + 2 * kGuardBand, c->pool, stream));
+    // canaries right before the first and right after the last byte the caller asked for
+    PHSH_CUDA(cudaMemsetAsync(base, 0xA5, kGuardBand, stream));
+    PHSH_CUDA(cudaMemsetAsync(static_cast<char*>(base) + kGuardBand + bytes, 0xA5, body - bytes + kGuardBand, stream));
+    p = static_cast<char*>(base) + kGuardBand;
+    guarded_bytes = bytes;
     return 0;
+}
+
+void DeviceBuf::release() {
+    if (!p) return;
+    if (guarded_bytes == 0) {
+        cudaFreeAsync(p, s);
+    } else {
+        const size_t body = (guarded_bytes + 255) & ~static_cast<size_t>(255);
+        char* base = static_cast<char*>(p) - kGuardBand;
+        const size_t tail = body - guarded_bytes + kGuardBand;
+        std::vector<unsigned char> h(kGuardBand + tail);
+        // the device must have finished with the buffer (on every stream of the lane) before the bands are read
+        bool ok = cudaDeviceSynchronize() == cudaSuccess &&
+                  cudaMemcpy(h.data(), base, kGuardBand, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                  cudaMemcpy(h.data() + kGuardBand, base + kGuardBand + guarded_bytes, tail, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok)
+            for (unsigned char b : h)
+                if (b != 0xA5) {
+                    ok = false;
+                    break;
+                }
+        g_guard_checked.fetch_add(1);
+        if (!ok) g_guard_violations.fetch_add(1);
+        cudaFreeAsync(base, s);
+    }
+    p = nullptr;
+    guarded_bytes = 0;
 }
 
 int HostLane::event(cudaEvent_t* out) {
@@ -512,6 +562,34 @@ int phsh_b200_rel_batch_host(const double* pot, long pot_stride, const int* jri,
     PHSH_CUDA(cudaStreamSynchronize(ln.sd));
     if (counters)
         for (int i = 0; i < 4; ++i) counters[i] += cnt[i];
+    return 0;
+}
+
+long phsh_b200_guard_violations(long* buffers_checked) {
+    if (buffers_checked) *buffers_checked = g_guard_checked.load();
+    return g_guard_violations.load();
+}
+
+int phsh_b200_guard_selftest(int device) {
+    int rc = select_device(device);
+    if (rc) return rc;
+    if (!guard_enabled()) {
+        set_error("PHSH_B200_GUARD is not set: the canary bands are off");
+        return PHSH_B200_EINVAL;
+    }
+    const long before = g_guard_violations.load();
+    for (int side = 0; side < 2; ++side) {
+        DeviceBuf b;
+        if ((rc = b.alloc(100, nullptr))) return rc;
+        // one byte past the end / one byte before the start
+        PHSH_CUDA(cudaMemset(static_cast<char*>(b.p) + (side == 0 ? 100 : -1), 0, 1));
+    }
+    const long seen = g_guard_violations.load() - before;
+    g_guard_violations.fetch_sub(seen);  // the two deliberate overruns do not count against the process
+    if (seen != 2) {
+        set_error("guard self test: %ld of 2 deliberate overruns detected", seen);
+        return PHSH_B200_ECUDA;
+    }
     return 0;
 }
 

@@ -27,13 +27,17 @@ int check_current_device();
 // stream-ordered scratch from the library's PRIVATE per-device memory pool (never the device's default pool, which
 // the embedding process -- e.g. torch's allocator -- may be sharing).  The pool keeps up to PHSH_B200_POOL_KEEP_MB
 // (default 4096) cached between calls; phsh_b200_trim() hands everything back to the driver.
+// With PHSH_B200_GUARD=1 in the environment every buffer gets a 256-byte canary band in front of and behind it, checked
+// when the buffer is released (compute-sanitizer is not available on the target pool; this is the library's own
+// out-of-bounds-write detector for its scratch and staging buffers, see phsh_b200_guard_violations).
 struct DeviceBuf {
     void* p = nullptr;
     cudaStream_t s = nullptr;
-    ~DeviceBuf() {
-        if (p) cudaFreeAsync(p, s);
-    }
+    size_t guarded_bytes = 0;  // > 0: p sits kGuardBand bytes inside a larger allocation
+    static constexpr size_t kGuardBand = 256;
+    ~DeviceBuf() { release(); }
     int alloc(size_t bytes, cudaStream_t stream);
+    void release();
 };
 
 // What a "_host" / "_file" entry point needs besides device memory: streams, events and (for pageable host buffers)

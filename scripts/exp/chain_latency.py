@@ -55,6 +55,30 @@ def cpu_chain():
     return t
 
 
+def reference_python_conphas():
+    """The reference's OWN conphas step (phaseshifts.conphas.Conphas, pure Python, staged under baseline/_ref): the same
+    work as the GPU chain's conphas step -- split phasout, parse, unwrap, write dataph_<name>.d and the cleed .phs --
+    which the oracle's step above does not do (it parses and unwraps, and writes nothing)."""
+    ref = os.path.join(os.path.dirname(__file__), "..", "..", "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "phaseshifts", "conphas.py")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from phaseshifts_b200 import backend
+    backend.install(force_standin=True)
+    from phaseshifts.conphas import Conphas as RefConphas
+    import io, contextlib
+    ts = []
+    for _ in range(7):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            files = RefConphas.split_phasout(P("phasout"), output_filenames=[P("RA.ph"), P("RB.ph")])
+            for f in files:
+                RefConphas(input_files=[f], output_file=f + "s", formatting="cleed", lmax=10).calculate()
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts) * 1e3)
+
+
 for _ in range(3):
     gpu_chain()
 g = [gpu_chain() for _ in range(15)]
@@ -64,4 +88,7 @@ gm, cm = med(g), med(c)
 a = [float(x) for l in open(P("A.phs")).read().splitlines()[2::2] for x in l.replace("-", " -").split()]
 print(json.dumps(dict(config="C1 chain: Re(0001) cluster -> cavpot x2 -> phsh_rel (2 x 57 x 13) -> conphas -> .phs, files in / files out",
                       gpu_ms=gm, gpu_total_ms=sum(gm.values()), cpu_oracle_ms=cm, cpu_oracle_total_ms=sum(cm.values()),
-                      cpu_threads=1, phs_values=len(a))))
+                      cpu_threads=1, phs_values=len(a),
+                      reference_python_conphas_ms=reference_python_conphas(),
+                      note="cpu_oracle_ms.conphas only parses and unwraps (no dataph_<name>.d, no .phs written); "
+                           "reference_python_conphas_ms is the reference's own Conphas doing what gpu_ms.conphas does")))
