@@ -327,14 +327,16 @@ def main():
     # DRAM traffic per launch and FP64-pipe utilisation come from the committed ncu --set full capture of this very
     # launch (profiles/); they are only quoted when the configuration is the captured one
     traffic, ncu_pipe = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_rel_integrate_ncu_c4.json")) as f:
-            cap = json.load(f)
-        if (P, NE, args.lmax, args.fast) == (4096, 1000, 15, False):
-            traffic = cap["traffic_bytes_per_launch"]
-            ncu_pipe = cap["fp64_pipe_pct_of_peak_sustained_active"]
-    except (OSError, KeyError, ValueError):
-        pass
+    for name in ("r2_rel_integrate_ncu_c4.json", "r1_rel_integrate_ncu_c4.json"):  # the latest committed capture
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                cap = json.load(f)
+            if (P, NE, args.lmax, args.fast) == (4096, 1000, 15, False):
+                traffic = cap["traffic_bytes_per_launch"]
+                ncu_pipe = cap["fp64_pipe_pct_of_peak_sustained_active"]
+            break
+        except (OSError, KeyError, ValueError):
+            continue
 
     # ---- end to end through the host-buffer C ABI (H2D + kernels + D2H inside the timed region) ------
     e2e_s, h2d, d2h, out_np = sh.e2e_seconds_per_step(args.steps, pinned=True)

@@ -126,6 +126,26 @@ def main():
                     units=S, gpu_ms=ms, gpu_units_per_s=S / ms * 1e3, cpu_units_per_s=n / cpu, cpu_threads=nt,
                     cpu_sample="first %d structures on %d threads" % (n, nt), cpu_single_thread_units_per_s=1.0 / cpu1,
                     max_abs_err=err, unit="structures"))
+    # C7: the atomic step in front of the producer -- hartfock on the reference's own Re input, then a batch of atoms
+    from oracle import hartfock_io as hio
+    re_in = os.path.join(ROOT, "tests", "golden", "Re0001", "atorb_Re")
+    spec = [v for c, v in hio.parse_atorb(re_in) if c == "a"][0]
+    atom = dict(z=75.0, nr=1000, rel=1.0, orbitals=spec["orbitals"])
+    api.hartfock_batch([atom])
+    t0 = time.perf_counter()
+    got = api.hartfock_batch([atom])[0]
+    ms1 = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    want = hio.scf(75.0, 1000, 1.0, 0.0, 0, spec)
+    cpu1 = time.perf_counter() - t0
+    nb = 148
+    t0 = time.perf_counter()
+    api.hartfock_batch([atom] * nb)
+    msb = (time.perf_counter() - t0) * 1e3
+    res.append(dict(config="C7 atomic step: hartfock for Re (22 orbitals x 1000 points, 17 SCF iterations), host API",
+                    units=1, gpu_ms=ms1, gpu_units_per_s=1e3 / ms1, cpu_units_per_s=1.0 / cpu1, cpu_threads=1,
+                    max_abs_err=float(np.abs(got["rho"] - want["rho"]).max()), bit_identical=bool(np.array_equal(got["rho"], want["rho"])),
+                    batch=dict(atoms=nb, gpu_ms=msb, atoms_per_s=nb / msb * 1e3), unit="atoms"))
     for r in res:
         r["speedup_vs_cpu_threads"] = r["gpu_units_per_s"] / r["cpu_units_per_s"]
         print(json.dumps(r), flush=True)

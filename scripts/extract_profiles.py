@@ -53,7 +53,7 @@ cap = {"kernel": "rel_integrate_kernel<false,double,6,false>", "workload": "C4: 
        "lanes_per_inst": get("smsp__thread_inst_executed_per_inst_executed.ratio")[0],
        "source": "ncu --set full --clock-control none -k regex:rel_integrate -s 3 -c 1 python bench.py --steps 1 "
                  "--warmup 3 --no-cpu-baseline (" + tag + ")"}
-json.dump(cap, open(os.path.join(P, "r1_rel_integrate_ncu_c4.json"), "w"), indent=1)
+json.dump(cap, open(os.path.join(P, tag + "_rel_integrate_ncu_c4.json"), "w"), indent=1)
 print(json.dumps(cap, indent=1))
 rows = list(csv.reader(open(os.path.join(G, "final_launches.csv"))))
 start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
