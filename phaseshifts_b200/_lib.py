@@ -42,7 +42,7 @@ class ConphasOpts(C.Structure):
 
 class CavpotBatch(C.Structure):
     _fields_ = [("n_struct", C.c_int), ("n_types", C.c_int), ("n_atoms", C.c_int), ("max_types", C.c_int),
-                ("max_atoms", C.c_int), ("type_off", C.c_void_p), ("atom_off", C.c_void_p), ("rc", C.c_void_p),
+                ("max_atoms", C.c_int), ("max_nh", C.c_int), ("type_off", C.c_void_p), ("atom_off", C.c_void_p), ("rc", C.c_void_p),
                 ("nrr", C.c_void_p), ("z", C.c_void_p), ("zc", C.c_void_p), ("rmt", C.c_void_p), ("dens", C.c_void_p),
                 ("rk", C.c_void_p), ("n_dens", C.c_int), ("rho", C.c_void_p), ("nx", C.c_void_p), ("alpha", C.c_void_p),
                 ("nh", C.c_void_p), ("slab", C.c_void_p), ("esht", C.c_void_p), ("nform", C.c_void_p)]
@@ -51,8 +51,7 @@ class CavpotBatch(C.Structure):
 class CavpotResult(C.Structure):
     _fields_ = [("mtz", C.c_void_p), ("npts", C.c_void_p), ("pot", C.c_void_p), ("pot_stride", C.c_long),
                 ("vh", C.c_void_p), ("vs", C.c_void_p), ("vmad", C.c_void_p), ("shell_ad", C.c_void_p),
-                ("shell_na", C.c_void_p), ("shell_ia", C.c_void_p), ("ncon", C.c_void_p), ("stats", C.c_void_p),
-                ("phase_clocks", C.c_void_p)]
+                ("shell_na", C.c_void_p), ("shell_ia", C.c_void_p), ("ncon", C.c_void_p), ("stats", C.c_void_p)]
 
 
 class HartfockAtom(C.Structure):

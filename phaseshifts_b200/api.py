@@ -492,9 +492,8 @@ def cavpot_batch(structures, rho, nx, *, diagnostics=False, device=0, on_device=
     if diagnostics:
         out.update(vh=np.zeros((T, 250)), vs=np.zeros((T, 250)), vmad=np.zeros((T, 250)), shell_ad=np.zeros((T, 30)),
                    shell_na=np.zeros((T, 30), dtype=np.int32), shell_ia=np.zeros((T, 30), dtype=np.int32),
-                   ncon=np.zeros(T, dtype=np.int32), stats=np.zeros((max(S, 0), 4), dtype=np.int32),
-                   phase_clocks=np.zeros((max(S, 0), 8), dtype=np.int64))
-        for k in ("vh", "vs", "vmad", "shell_ad", "shell_na", "shell_ia", "ncon", "stats", "phase_clocks"):
+                   ncon=np.zeros(T, dtype=np.int32), stats=np.zeros((max(S, 0), 4), dtype=np.int32))
+        for k in ("vh", "vs", "vmad", "shell_ad", "shell_na", "shell_ia", "ncon", "stats"):
             setattr(r, k, out[k].ctypes.data)
     _lib.check(_lib.load().phsh_b200_cavpot_batch_host(C.byref(b), C.byref(r), ASBUILT if asbuilt else 0, int(device)))
     out["vhar"], out["vex"] = out["mtz2"][:, 0].copy(), out["mtz2"][:, 1].copy()
@@ -519,6 +518,7 @@ def _cavpot_batch_device(keep, S, T, A, n_dens, device, flags=0):
     b.n_struct, b.n_types, b.n_atoms, b.n_dens = S, T, A, n_dens
     b.max_types = int(np.diff(to).max()) if S else 1
     b.max_atoms = int(np.diff(ao).max()) if S else 1
+    b.max_nh = int(keep["nh"].max()) if S else 0
     for k, v in d.items():
         setattr(b, k, v.data_ptr())
     mtz = torch.zeros((S, 2), dtype=torch.float64, device=dev)

@@ -351,8 +351,7 @@ static int launch_rel_integrate(const double* pot, long pot_stride, const int* j
 template <class Real>
 static int launch_rel_energy_axis(const double* raw, int P, int NE, int lsm, int flags, double* delta, cudaStream_t st) {
     const int L1 = lsm + 1;
-    const long warps = static_cast<long>(P) * L1;
-    rel_energy_axis_kernel<Real><<<static_cast<unsigned>((warps + 3) / 4), 128, 0, st>>>(
+    rel_energy_axis_kernel<Real><<<static_cast<unsigned>(P) * axis_groups(L1), axis_threads(L1), 0, st>>>(
         raw, P, L1, NE, (flags & PHSH_B200_UNWRAP) ? 1 : 0, delta);
     PHSH_CUDA(cudaGetLastError());
     return 0;
@@ -611,9 +610,8 @@ int phsh_b200_conphas_device(const double* phas, int P, int NE, int L, int lmax,
     if (P == 0 || NE == 0) return 0;
     int rc = check_current_device();
     if (rc) return rc;
-    const long warps = static_cast<long>(P) * L;
-    conphas_kernel<<<static_cast<unsigned>((warps + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(phas, P, NE, L,
-                                                                                                        lmax, out);
+    conphas_kernel<<<static_cast<unsigned>(P) * axis_groups(L), axis_threads(L), 0, static_cast<cudaStream_t>(stream)>>>(
+        phas, P, NE, L, lmax, out);
     PHSH_CUDA(cudaGetLastError());
     return 0;
 }

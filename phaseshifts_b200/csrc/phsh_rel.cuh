@@ -518,98 +518,169 @@ __device__ __forceinline__ int conphas_jump(double cur, double prev) {
     return 0;
 }
 
+// Both energy-axis kernels walk [P][NE][L]-ordered results with one warp per (potential, l).  A warp's own element of an
+// energy row is L*8 bytes away from its neighbour's, so the warps of up to kAxisLG consecutive l share a CTA and pass
+// kAxisU 32-energy tiles at a time through shared memory: the global accesses are then whole runs of the reference's
+// JF(NE, L) rows, and every warp has kAxisU independent loads in flight per barrier pair.
+constexpr int kAxisLG = 16;
+constexpr int kAxisU = 4;
+constexpr int kAxisRows = 32 * kAxisU;
+__host__ __device__ inline int axis_groups(int L) { return (L + kAxisLG - 1) / kAxisLG; }
+__host__ __device__ inline int axis_threads(int L) { return 32 * (L < kAxisLG ? L : kAxisLG); }
+__device__ __forceinline__ void axis_store_tile(const double (*tile)[kAxisLG + 1], double* __restrict__ rows, int L, int l0,
+                                                int Lg, int ne_t) {
+    for (int idx = threadIdx.x; idx < ne_t * Lg; idx += blockDim.x) {
+        const int e = idx / Lg, j = idx - e * Lg;
+        rows[static_cast<size_t>(e) * L + l0 + j] = tile[e][j];
+    }
+}
+
 template <class Real>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * kAxisLG)
     rel_energy_axis_kernel(const double* __restrict__ raw, int P, int L1, int NE, int unwrap,
                            double* __restrict__ delta) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= P * L1) return;
-    const int p = warp / L1, l = warp % L1;
+    __shared__ double tile[kAxisRows][kAxisLG + 1];
+    const int groups = axis_groups(L1);
+    const int p = blockIdx.x / groups, l0 = (blockIdx.x - p * groups) * kAxisLG;
+    const int Lg = min(kAxisLG, L1 - l0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool wact = warp < Lg;
+    const int l = l0 + (wact ? warp : 0);
     const double2* src = reinterpret_cast<const double2*>(raw) + (static_cast<size_t>(p) * L1 + l) * NE;
     unsigned state = 1;  // LVOR = 0
     int ifak = 0;
     double prev_last = 0.0;
     const double pi = 3.141592653589793;
-    for (int base = 0; base < NE; base += 32) {
-        const int ie = base + lane;
-        const bool act = ie < NE;
-        double2 v = make_double2(0.0, 0.0);
-        if (act) v = src[ie];
-        Real cand[3];
-        unsigned f = kMapIdentity;
-        if (l == 0) {
-            cand[0] = cand[1] = cand[2] = static_cast<Real>(v.x);
-        } else if (act) {
-            f = 0;
+    for (int base0 = 0; base0 < NE; base0 += kAxisRows) {
+        double2 vv[kAxisU];
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
+        for (int u = 0; u < kAxisU; ++u) {
+            const int ie = base0 + 32 * u + lane;
+            vv[u] = (wact && ie < NE) ? src[ie] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < kAxisU; ++u) {
+            const int base = base0 + 32 * u;
+            if (base >= NE) break;
+            const int ie = base + lane;
+            const bool act = wact && ie < NE;
+            const double2 v = vv[u];
+            // Candidate outputs for the three incoming LVOR states.  Unless |JFD-JFU| > 2.5 (ZFDIFF = -(JFD-JFU)*LVOR beyond
+            // +-2.5 for LVOR = +-1, libphsh.f:4684-4687) LK is 0 for every state, all three candidates are the LVOR = 0
+            // one and the lane's map is constant (LVOR' = sign of JFS): one evaluation instead of three.
+            Real cand[3];
+            unsigned f = kMapIdentity;
+            bool depends = false;  // this lane's output depends on the incoming state
+            if (l == 0) {
+                cand[0] = cand[1] = cand[2] = static_cast<Real>(v.x);
+                depends = false;
+            } else if (act) {
+                const Real jfd = static_cast<Real>(v.x), jfu = static_cast<Real>(v.y);
                 int out;
-                rel_combine<Real>(static_cast<Real>(v.x), static_cast<Real>(v.y), l, s - 1, cand[s], out);
-                f |= static_cast<unsigned>(out + 1) << (2 * s);
+                rel_combine<Real>(jfd, jfu, l, 0, cand[1], out);
+                const double zf = static_cast<double>(RMath<Real>::sub(jfd, jfu));
+                if (zf > static_cast<double>(2.5f) || zf < static_cast<double>(-2.5f)) {
+                    int om, op;
+                    rel_combine<Real>(jfd, jfu, l, -1, cand[0], om);
+                    rel_combine<Real>(jfd, jfu, l, 1, cand[2], op);
+                    f = static_cast<unsigned>(om + 1) | (static_cast<unsigned>(out + 1) << 2) | (static_cast<unsigned>(op + 1) << 4);
+                    depends = true;
+                } else {
+                    cand[0] = cand[2] = cand[1];
+                    f = static_cast<unsigned>(out + 1) * 21u;  // the same image for the three states
+                }
+            } else {
+                cand[0] = cand[1] = cand[2] = 0;
             }
-        } else {
-            cand[0] = cand[1] = cand[2] = 0;
-        }
-        // inclusive scan of map composition across the warp
-        unsigned F = f;
+            double jfs;
+            if (l == 0 || !__any_sync(0xffffffffu, depends)) {
+                // no lane of this tile looks at its incoming state: no scan needed; the state after the tile is the image
+                // of the last lane's (constant) map -- lanes beyond NE carry the identity, so go through map_apply
+                jfs = static_cast<double>(cand[1]);
+                if (l != 0) {
+                    const int last_lane = min(31, NE - 1 - base);
+                    state = map_apply(__shfl_sync(0xffffffffu, f, last_lane), state);
+                }
+            } else {
+                // inclusive scan of map composition across the warp
+                unsigned F = f;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned G = __shfl_up_sync(0xffffffffu, F, o);
-            if (lane >= o) F = map_compose(G, F);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned G = __shfl_up_sync(0xffffffffu, F, o);
+                    if (lane >= o) F = map_compose(G, F);
+                }
+                unsigned Fex = __shfl_up_sync(0xffffffffu, F, 1);
+                if (lane == 0) Fex = kMapIdentity;
+                const unsigned s_in = map_apply(Fex, state);
+                jfs = static_cast<double>(s_in == 0 ? cand[0] : (s_in == 1 ? cand[1] : cand[2]));
+                state = map_apply(__shfl_sync(0xffffffffu, F, 31), state);
+            }
+            double outv = jfs;
+            if (unwrap) {
+                double prev = __shfl_up_sync(0xffffffffu, jfs, 1);
+                if (lane == 0) prev = prev_last;
+                int j = (act && ie > 0) ? conphas_jump(jfs, prev) : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, j, o);
+                    if (lane >= o) j += t;
+                }
+                const int my = ifak + j;
+                outv = __dadd_rn(jfs, __dmul_rn(pi, static_cast<double>(my)));
+                ifak += __shfl_sync(0xffffffffu, j, 31);
+                const int last = min(31, NE - 1 - base);
+                prev_last = __shfl_sync(0xffffffffu, jfs, last);
+            }
+            if (wact) tile[32 * u + lane][warp] = outv;
         }
-        unsigned Fex = __shfl_up_sync(0xffffffffu, F, 1);
-        if (lane == 0) Fex = kMapIdentity;
-        const unsigned s_in = map_apply(Fex, state);
-        const double jfs = static_cast<double>(s_in == 0 ? cand[0] : (s_in == 1 ? cand[1] : cand[2]));
-        state = map_apply(__shfl_sync(0xffffffffu, F, 31), state);
-        double outv = jfs;
-        if (unwrap) {
-            double prev = __shfl_up_sync(0xffffffffu, jfs, 1);
+        __syncthreads();
+        axis_store_tile(tile, delta + (static_cast<size_t>(p) * NE + base0) * L1, L1, l0, Lg, min(kAxisRows, NE - base0));
+        __syncthreads();
+    }
+}
+
+// conphas on an arbitrary [P][NE][L] array (cav path, stand-alone API); one warp per (p, l), out may alias phas
+__global__ void __launch_bounds__(32 * kAxisLG)
+    conphas_kernel(const double* phas, int P, int NE, int L, int lmax, double* out) {
+    __shared__ double tile[kAxisRows][kAxisLG + 1];
+    const int groups = axis_groups(L);
+    const int p = blockIdx.x / groups, l0 = (blockIdx.x - p * groups) * kAxisLG;
+    const int Lg = min(kAxisLG, L - l0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool wact = warp < Lg;
+    const int l = l0 + (wact ? warp : 0);
+    const double pi = 3.141592653589793;
+    int ifak = 0;
+    double prev_last = 0.0;
+    for (int base0 = 0; base0 < NE; base0 += kAxisRows) {
+        const int ne_t = min(kAxisRows, NE - base0);
+        const double* rows = phas + (static_cast<size_t>(p) * NE + base0) * L;
+        for (int idx = threadIdx.x; idx < ne_t * Lg; idx += blockDim.x) {
+            const int e = idx / Lg, j = idx - e * Lg;
+            tile[e][j] = rows[static_cast<size_t>(e) * L + l0 + j];
+        }
+        __syncthreads();
+        for (int base = base0; base < base0 + ne_t; base += 32) {
+            const int ie = base + lane;
+            const bool act = wact && ie < NE;
+            const double v = act ? tile[ie - base0][warp] : 0.0;
+            double prev = __shfl_up_sync(0xffffffffu, v, 1);
             if (lane == 0) prev = prev_last;
-            int j = (act && ie > 0) ? conphas_jump(jfs, prev) : 0;
+            int j = (act && ie > 0 && l <= lmax) ? conphas_jump(v, prev) : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, j, o);
                 if (lane >= o) j += t;
             }
             const int my = ifak + j;
-            outv = __dadd_rn(jfs, __dmul_rn(pi, static_cast<double>(my)));
+            if (act) tile[ie - base0][warp] = (l <= lmax) ? __dadd_rn(v, __dmul_rn(pi, static_cast<double>(my))) : v;
             ifak += __shfl_sync(0xffffffffu, j, 31);
             const int last = min(31, NE - 1 - base);
-            prev_last = __shfl_sync(0xffffffffu, jfs, last);
+            prev_last = __shfl_sync(0xffffffffu, v, last);
         }
-        if (act) delta[(static_cast<size_t>(p) * NE + ie) * L1 + l] = outv;
-    }
-}
-
-// conphas on an arbitrary [P][NE][L] array (cav path, stand-alone API); one warp per (p, l)
-__global__ void __launch_bounds__(128)
-    conphas_kernel(const double* __restrict__ phas, int P, int NE, int L, int lmax, double* __restrict__ out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= P * L) return;
-    const int p = warp / L, l = warp % L;
-    const double pi = 3.141592653589793;
-    int ifak = 0;
-    double prev_last = 0.0;
-    for (int base = 0; base < NE; base += 32) {
-        const int ie = base + lane;
-        const bool act = ie < NE;
-        const double v = act ? phas[(static_cast<size_t>(p) * NE + ie) * L + l] : 0.0;
-        double prev = __shfl_up_sync(0xffffffffu, v, 1);
-        if (lane == 0) prev = prev_last;
-        int j = (act && ie > 0 && l <= lmax) ? conphas_jump(v, prev) : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, j, o);
-            if (lane >= o) j += t;
-        }
-        const int my = ifak + j;
-        if (act) out[(static_cast<size_t>(p) * NE + ie) * L + l] = (l <= lmax) ? __dadd_rn(v, __dmul_rn(pi, static_cast<double>(my))) : v;
-        ifak += __shfl_sync(0xffffffffu, j, 31);
-        const int last = min(31, NE - 1 - base);
-        prev_last = __shfl_sync(0xffffffffu, v, last);
+        __syncthreads();
+        axis_store_tile(tile, out + (static_cast<size_t>(p) * NE + base0) * L, L, l0, Lg, ne_t);
+        __syncthreads();
     }
 }
 
