@@ -289,6 +289,47 @@ def test_fine_sampling_grid_spans_many_passes(re_case):
     _check(many, 200, ref, 2)
 
 
+def test_every_route_through_the_muffin_tin_zero_gives_the_same_bits(re_case, monkeypatch):
+    """MTZ's interstitial points go through one flat list over the batch (chunked when the list would not fit the scratch
+    budget) or, for sample grids that are doubled / too fine for the list / of unknown size, through the in-CTA form:
+    VHAR, VEX and the potentials must not depend on the route.  NH = 41 is beyond the list's limit (40) and is checked
+    against the oracle directly."""
+    from oracle import cavpot_io as cio
+    from phaseshifts_b200 import api
+    cl, _, rho, nx = re_case
+    rng = np.random.default_rng(5)
+    structs = []
+    for s in range(300):
+        c = dict(cl)
+        c["spa"] = cl["spa"] * (1 + 0.03 * rng.uniform(-1, 1))
+        c["rmt"] = cl["rmt"] * (1 + 0.05 * rng.uniform(-1, 1, size=2))
+        c["nh"] = int(rng.choice([1, 3, 6, 10]))
+        structs.append(_struct(c))
+    ref = api.cavpot_batch(structs, rho, nx, diagnostics=True)
+    assert (ref["stats"][:, 0] > 0).all()
+    monkeypatch.setenv("PHSH_B200_CAVPOT_LIST_MB", "1")     # 1 MB / (1000 entries * 20 B) -> chunks of 52 structures
+    chunked = api.cavpot_batch(structs, rho, nx, diagnostics=True)
+    monkeypatch.delenv("PHSH_B200_CAVPOT_LIST_MB")
+    monkeypatch.setenv("PHSH_B200_CAVPOT_INCTA", "1")
+    incta = api.cavpot_batch(structs, rho, nx, diagnostics=True)
+    monkeypatch.delenv("PHSH_B200_CAVPOT_INCTA")
+    for other in (chunked, incta):
+        for k in ("vhar", "vex", "pot", "npts", "stats"):
+            assert np.array_equal(ref[k], other[k]), k
+    for s in (0, 17, 299):
+        c = dict(cl, spa=structs[s]["spa"], rmt=structs[s]["rmt"], nh=structs[s]["nh"])
+        o = cio.cavpot(c, rho, nx, real32=False)
+        # VHAR is add/mul/div/sqrt only (bit-identical); VEX goes through pow (CUDA's vs glibc's: a few ulp per point)
+        assert ref["vhar"][s] == o["vhar"], (s, ref["vhar"][s], o["vhar"])
+        assert abs(ref["vex"][s] - o["vex"]) <= 1e-13 * abs(o["vex"]), (s, ref["vex"][s], o["vex"])
+        assert list(ref["stats"][s][:2]) == [o["nint"], o["npoint"]]
+    c = dict(cl)
+    c["nh"] = 41
+    o = cio.cavpot(c, rho, nx, real32=False)
+    fine = api.cavpot_batch([_struct(c)] * 2, rho, nx, diagnostics=True)
+    assert fine["vhar"][1] == o["vhar"] and fine["vex"][1] == o["vex"] and list(fine["stats"][1][:2]) == [o["nint"], o["npoint"]]
+
+
 def test_many_atom_types_in_both_launch_configurations(re_case):
     """20 atom types / 40 atoms in a large cell (154 KB of shared memory per CTA): alone (one 512-thread CTA) and as part of
     a 150-structure batch (128-thread CTAs) -- same bits either way, and equal to the oracle."""
