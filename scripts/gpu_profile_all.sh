@@ -19,19 +19,26 @@ $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final_launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 cut -c1-200 gpurun_out/final_bench_n1.json
 else
+# ncu --set full captures; the reports are turned into raw-metric and SASS-source CSVs on the box (gpurun_out/ is capped at
+# 64 MiB), only the rel_integrate report itself is kept
+cap() {  # cap <name> <kernel regex> <skip> <command...>
+  local name=$1 rx=$2 skip=$3; shift 3
+  ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c 1 -f -o gpurun_out/final_prof_$name "$@" > gpurun_out/ncu_$name.log 2>&1
+  ncu -i gpurun_out/final_prof_$name.ncu-rep --page raw --csv > gpurun_out/final_prof_${name}_raw.csv 2>/dev/null
+  ncu -i gpurun_out/final_prof_$name.ncu-rep --page source --csv > gpurun_out/final_prof_${name}_source.csv 2>/dev/null
+  [ "$name" = rel ] || rm -f gpurun_out/final_prof_$name.ncu-rep
+  tail -1 gpurun_out/ncu_$name.log | cut -c1-160
+}
 CMD2="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
-$CMD2 > gpurun_out/ncu_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:rel_integrate -s 3 -c 1 -o gpurun_out/final_prof_rel $CMD2 > gpurun_out/ncu_full.log 2>&1
-ncu --set full --clock-control none -k regex:rel_energy_axis -s 3 -c 1 -o gpurun_out/final_prof_axis $CMD2 > gpurun_out/ncu_axis.log 2>&1
-python scripts/exp/cav_one_launch.py > gpurun_out/cav_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:cav_ps_kernel -s 1 -c 1 -o gpurun_out/final_prof_cav python scripts/exp/cav_one_launch.py > gpurun_out/ncu_cav.log 2>&1
+$CMD2 > gpurun_out/ncu_plain2.log 2>&1 || exit 1
+cap rel rel_integrate 3 $CMD2
+cap axis rel_energy_axis 3 $CMD2
+python scripts/exp/cav_one_launch.py > gpurun_out/cav_plain.log 2>&1 && cap cav cav_ps_kernel 1 python scripts/exp/cav_one_launch.py
 CMD3="python scripts/exp/cavpot_dev_time.py 4096 2"
-$CMD3 > gpurun_out/cavpot_plain.log 2>&1 &&
-for k in prep sumax classify mtz_sum finish; do
-ncu --set full --clock-control none --import-source on -k regex:cavpot_${k} -s 1 -c 1 -f -o gpurun_out/final_prof_cavpot_$k $CMD3 > gpurun_out/ncu_cavpot_$k.log 2>&1
-done
+$CMD3 > gpurun_out/cavpot_plain.log 2>&1 || exit 1
+for k in prep sumax classify mtz_sum finish; do cap cavpot_$k cavpot_$k 1 $CMD3; done
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final_cavpot_launches.csv $CMD3 > gpurun_out/ncu_cavpot_launch.log 2>&1
-python scripts/exp/wil_time.py > gpurun_out/wil_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:wil_integrate -s 1 -c 1 -f -o gpurun_out/final_prof_wil python scripts/exp/wil_time.py > gpurun_out/ncu_wil.log 2>&1
-tail -2 gpurun_out/ncu_full.log gpurun_out/ncu_axis.log gpurun_out/ncu_cav.log gpurun_out/ncu_cavpot_*.log gpurun_out/ncu_wil.log | cut -c1-200; cat gpurun_out/cavpot_plain.log
+python scripts/exp/wil_time.py > gpurun_out/wil_plain.log 2>&1 && cap wil wil_integrate 1 python scripts/exp/wil_time.py
+cat gpurun_out/cavpot_plain.log gpurun_out/wil_plain.log
+du -sh gpurun_out
 fi
