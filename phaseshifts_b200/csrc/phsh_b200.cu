@@ -1,6 +1,7 @@
 // phsh_b200.cu -- C-ABI entry points (include/phsh_b200.h) and launch logic for the sm_100a kernels.
 // There is deliberately no CPU implementation here: without a CUDA device every compute call fails.
 #include <cmath>
+#include <ctime>
 #include <cstdlib>
 #include <algorithm>
 #include <cstring>
@@ -28,6 +29,29 @@ void set_error(const char* fmt, ...) {
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     g_err = buf;
+}
+
+static double trace_now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+Trace::Trace(const char* entry_name) : entry(entry_name), on(false), t0(0.0), last(0.0) {
+    static const bool enabled = [] {
+        const char* e = getenv("PHSH_B200_TRACE");
+        return e != nullptr && atoi(e) > 0;
+    }();
+    on = enabled;
+    if (on) t0 = last = trace_now_ms();
+}
+void Trace::mark(const char* stage) {
+    if (!on) return;
+    const double t = trace_now_ms();
+    fprintf(stderr, "[phsh_b200] %s: %s %.3f ms\n", entry, stage, t - last);
+    last = t;
+}
+Trace::~Trace() {
+    if (on) fprintf(stderr, "[phsh_b200] %s: total %.3f ms\n", entry, trace_now_ms() - t0);
 }
 
 int cuda_fail(cudaError_t e, const char* what) {

@@ -20,6 +20,17 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return ::phsh::cuda_fail(_e, #call);  \
     } while (0)
 
+// Stage timing of the file entry points: with PHSH_B200_TRACE=1 in the environment every stage boundary prints one line
+// "[phsh_b200] <entry>: <stage> <ms>" to stderr (wall clock; the device stages include their synchronisation).
+struct Trace {
+    const char* entry;
+    bool on;
+    double t0, last;
+    explicit Trace(const char* entry_name);
+    void mark(const char* stage);
+    ~Trace();
+};
+
 // make `device` current and check that it is a Blackwell sm_100 part; returns 0 or a PHSH_B200_E* code
 int select_device(int device);
 int check_current_device();

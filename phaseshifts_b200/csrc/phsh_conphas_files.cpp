@@ -249,6 +249,7 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
         set_error("bad arguments");
         return PHSH_B200_EINVAL;
     }
+    phsh::Trace trace("conphas_files");
     const int device = opts ? opts->device : 0;
     std::string fmtname = format ? format : "";
     for (char& c : fmtname) c = static_cast<char>(tolower(static_cast<unsigned char>(c)));
@@ -298,10 +299,12 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
         std::vector<double> in(static_cast<size_t>(n_phases) * L), out(in.size());
         for (int ie = 0; ie < n_phases; ++ie)
             for (int l = 0; l < L; ++l) in[static_cast<size_t>(ie) * L + l] = S.phas[ie][l];
+        trace.mark("read + parse input");
         if (n_phases > 0) {
             const int rc = phsh_b200_conphas_host(in.data(), 1, n_phases, L, lmax > 18 ? 18 : lmax, out.data(), device);
             if (rc) return rc;
         }
+        trace.mark("device (H2D, conphas_kernel, D2H)");
         conpha[i].assign(n_phases, std::vector<double>(L));
         for (int ie = 0; ie < n_phases; ++ie)
             for (int l = 0; l < L; ++l) conpha[i][ie][l] = out[static_cast<size_t>(ie) * L + l];
@@ -333,6 +336,7 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
             fwrite(txt.data(), 1, txt.size(), f);
         }
         fclose(f);
+        trace.mark("write dataph_<name>.d");
     }
     // conphas.py:434 re-runs `conpha = deepcopy(phas)` for every input file, which throws away the unwrapping of
     // all earlier files: only the last input is written unwrapped.  Reproduced unless asked otherwise.
@@ -436,6 +440,7 @@ static int conphas_files_impl(const char* const* inputs, int n_inputs, const cha
         fwrite(txt.data(), 1, txt.size(), f);
     }
     fclose(f);
+    trace.mark("write output file");
     return 0;
 }
 

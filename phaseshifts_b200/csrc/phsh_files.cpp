@@ -289,6 +289,7 @@ static int phsh_b200_rel_file_impl(const char* mufftin, const char* phasout, con
         set_error("NULL path");
         return PHSH_B200_EINVAL;
     }
+    phsh::Trace trace("rel_file");
     std::vector<std::string> lines;
     if (!read_lines(mufftin, &lines)) {  // Fortran: open(status='old') failure aborts the process; we report
         set_error("cannot open mufftin file '%s'", mufftin);
@@ -358,6 +359,7 @@ static int phsh_b200_rel_file_impl(const char* mufftin, const char* phasout, con
         i += 3 + nrec;
     }
     inp += "\n\n" + std::string(56, ' ') + "end OF INPUT data\n";
+    trace.mark("read + parse mufftin, inpdat echo");
 
     // batch blocks that share (N, LSM) and the energy grid into one launch
     std::vector<std::vector<double>> jf(blocks.size());
@@ -397,12 +399,14 @@ static int phsh_b200_rel_file_impl(const char* mufftin, const char* phasout, con
         }
     }
 
+    trace.mark("device (H2D, kernels, D2H)");
     Out fp, fd, fi;
     if (!fp.open(phasout) || !fd.open(dataph) || !fi.open(inpdat)) {
         set_error("cannot open an output file for writing ('%s', '%s' or '%s')", phasout, dataph, inpdat);
         return PHSH_B200_EIO;
     }
     fi.put(inp);
+    trace.mark("open outputs, write inpdat");
     for (size_t bi = 0; bi < blocks.size(); ++bi) {
         const RelBlock& b = blocks[bi];
         const int L1 = b.lsm + 1;
@@ -433,6 +437,7 @@ static int phsh_b200_rel_file_impl(const char* mufftin, const char* phasout, con
             fd.put("\n");
         }
     }
+    trace.mark("format phasout + dataph");
     return 0;
 }
 
