@@ -26,12 +26,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "phsh_cav.cuh"  // div_tracked / DivTrack
+
 namespace phsh {
 
 constexpr int kHfMaxOrb = 33;     // iorbs (libphsh.f:63)
 constexpr int kHfMaxNr = 4000;    // nrmax
 constexpr int kHfMaxEvents = 64;  // rescalings of one outward sweep kept for the parallel fix-up
 constexpr int kHfMaxStack = 48;   // sweeps of one bisection whose phi entries survive (see elsolve below)
+constexpr int kHfThreads = 768;
 
 struct HfTerm {   // one (i, j, la) term of getpot's pair loops, in the reference's order
     int i, j, la, kind;  // kind 0 = direct Coulomb (:473-538), 1 = exchange (:548-613); i, j 0-based
@@ -46,6 +49,7 @@ struct HfProblem {  // one atom; every pointer is a DEVICE pointer into this ato
     double xnj[kHfMaxOrb], occ[kHfMaxOrb];
     const double *r, *dr, *r2, *rpower;  // [nr], rpower [8][nr]
     double *phe, *orb, *v, *xm1, *xm2, *phi2;  // [nel][nr]
+    double* xkr;                                 // [nel][nr] xkappa(orbital) / r: the energy-independent quotient of integ
     double *contrib;                            // [nterms][2][nr]
     const HfTerm* terms;
     const int* upd_off;   // [nel+1]
@@ -63,36 +67,56 @@ struct HfIntegConsts {
 // integ (libphsh.f:992-1165) with istop = 0 on entry.  Returns the verdict (ief after elsolve's node-count override,
 // :763) and, in `reach`, the last index of phi the sweep assigns.  WRITE = true also stores phi, with the |p2| > 1e10
 // rescalings recorded so that the warp can apply them in parallel afterwards.
-template <bool WRITE>
-__device__ int hf_integ(double e, const HfIntegConsts& c, const double* __restrict__ v, const double* __restrict__ xm1,
-                        const double* __restrict__ xm2, const double* __restrict__ r, const double* __restrict__ r2,
-                        double* phi, int* ev_idx, double* ev_div, int& nev, int& reach) {
+//
+// The sweep is a 1000-step recurrence per lane and the whole atomic step is bound by its latency, so it is arranged for
+// instruction-level parallelism without changing one rounding:
+//   * the coefficients of a step -- t, xm, tm, xm1/xm, xm2/tm, xk, dk (:1075-1084) -- do not depend on the recurrence:
+//     they are evaluated two mesh points at a time, ahead of the two recurrence steps that consume them, so that two
+//     independent chains (and the short recurrence chain) are in flight together;
+//   * xkappa/r(i) is the same for every energy: tabulated once per orbital (`xkr`);
+//   * the quotients run as the fast path of the library's IEEE division without its per-division range test (div_tracked of
+//     phsh_cav.cuh: hi words folded into running minima / maxima); a sweep whose operands left the validity window reports
+//     ok = false and is repeated with __ddiv_rn (EXACT).  NONREL (a2 == 0: xm == 1 and tm == 2 exactly) replaces the two
+//     coefficient quotients by x and x/2, which is what the divisions return.
+template <bool WRITE, bool EXACT, bool NONREL>
+__device__ __noinline__ int hf_integ(double e, const HfIntegConsts& c, const double* __restrict__ v,
+                                     const double* __restrict__ xm1, const double* __restrict__ xm2,
+                                     const double* __restrict__ xkr, const double* __restrict__ r,
+                                     const double* __restrict__ r2, double* phi, int* ev_idx, double* ev_div, int& nev,
+                                     int& reach, bool& ok) {
     const int nr = c.nr;
-    double t = __dsub_rn(e, v[0]);
-    const double xm0 = __dadd_rn(1.0, __dmul_rn(c.a2, t));
-    double tm = __dadd_rn(xm0, xm0);
-    double xmx = __ddiv_rn(xm1[0], xm0);
-    const double xk0 = __dsub_rn(
-        __dmul_rn(r2[0], __dadd_rn(__dsub_rn(__dmul_rn(tm, t),
-                                             __dmul_rn(xmx, __dadd_rn(__ddiv_rn(c.xkappa, r[0]), __dmul_rn(0.75, xmx)))),
-                                   __ddiv_rn(xm2[0], tm))),
-        c.xl4);
-    const double dk0 = __dadd_rn(1.0, __dmul_rn(c.dl2, xk0));
+    DivTrack trk;
+    trk.reset();
+    auto dv = [&](double x, double a) { return EXACT ? __ddiv_rn(x, a) : div_tracked(x, a, trk); };
+    // coefficients of mesh point i (1-based): xk, dk and, for WRITE, sqrt(xm r) of phi's normalisation; xm is returned too
+    auto coef = [&](int i, double& xk, double& dk, double& sq, double& xm) {
+        const double t = __dsub_rn(e, v[i - 1]);
+        xm = __dadd_rn(1.0, __dmul_rn(c.a2, t));
+        const double tm = __dadd_rn(xm, xm);
+        double xmx, q4;
+        if (NONREL) {
+            xmx = xm1[i - 1];
+            q4 = __dmul_rn(xm2[i - 1], 0.5);
+        } else {
+            xmx = dv(xm1[i - 1], xm);
+            q4 = dv(xm2[i - 1], tm);
+        }
+        xk = __dsub_rn(
+            __dmul_rn(r2[i - 1], __dadd_rn(__dsub_rn(__dmul_rn(tm, t), __dmul_rn(xmx, __dadd_rn(xkr[i - 1], __dmul_rn(0.75, xmx)))),
+                                           q4)),
+            c.xl4);
+        dk = __dadd_rn(1.0, __dmul_rn(c.dl2, xk));
+        sq = WRITE ? sqrt(__dmul_rn(xm, r[i - 1])) : 0.0;
+    };
+    double xk0, dk0, sq0, xm0;
+    coef(1, xk0, dk0, sq0, xm0);
     double p0 = dk0;
-    if (WRITE) phi[0] = __ddiv_rn(__dmul_rn(p0, sqrt(__dmul_rn(xm0, r[0]))), dk0);
-    t = __dsub_rn(e, v[1]);
-    double xm = __dadd_rn(1.0, __dmul_rn(c.a2, t));
-    tm = __dadd_rn(xm, xm);
-    xmx = __ddiv_rn(xm1[1], xm);
-    double xk2 = __dsub_rn(
-        __dmul_rn(r2[1], __dadd_rn(__dsub_rn(__dmul_rn(tm, t),
-                                             __dmul_rn(xmx, __dadd_rn(__ddiv_rn(c.xkappa, r[1]), __dmul_rn(0.75, xmx)))),
-                                   __ddiv_rn(xm2[1], tm))),
-        c.xl4);
-    double dk2 = __dadd_rn(1.0, __dmul_rn(c.dl2, xk2));
+    if (WRITE) phi[0] = __ddiv_rn(__dmul_rn(p0, sq0), dk0);
+    double xk2, dk2, sq2, xm;
+    coef(2, xk2, dk2, sq2, xm);
     double p1 = __dmul_rn(
         __dmul_rn(dk2, __dsub_rn(c.pw12, __ddiv_rn(__dmul_rn(__dsub_rn(r[1], r[0]), c.z), c.xlp))), sqrt(__ddiv_rn(xm0, xm)));
-    if (WRITE) phi[1] = __ddiv_rn(__dmul_rn(p1, sqrt(__dmul_rn(xm, r[1]))), dk2);
+    if (WRITE) phi[1] = __ddiv_rn(__dmul_rn(p1, sq2), dk2);
     // classical turning point (:1059-1068)
     int istop = 0;
     for (int j = nr - 1; j >= 2; --j)
@@ -101,25 +125,18 @@ __device__ int hf_integ(double e, const HfIntegConsts& c, const double* __restri
             break;
         }
     reach = 2;
+    ok = true;
     if (istop == 0) return -1;
     int nn = 0;
     // the two loops of the Fortran (3..istop+2 and istop+3..nr-1) differ only by the blow-up test of the second
     const int last = max(min(istop + 2, nr), nr - 1);
-    for (int i = 3; i <= last; ++i) {
-        t = __dsub_rn(e, v[i - 1]);
-        xm = __dadd_rn(1.0, __dmul_rn(c.a2, t));
-        tm = __dadd_rn(xm, xm);
-        xmx = __ddiv_rn(xm1[i - 1], xm);
-        double p2 = __dsub_rn(__ddiv_rn(__dmul_rn(__dsub_rn(2.0, __dmul_rn(c.dl5, xk2)), p1), dk2), p0);
+    // one recurrence step at mesh point i with the coefficients (xkN, dkN, sqN) of that point; 2 = go on
+    auto step = [&](int i, double xkN, double dkN, double sqN) -> int {
+        double p2 = __dsub_rn(dv(__dmul_rn(__dsub_rn(2.0, __dmul_rn(c.dl5, xk2)), p1), dk2), p0);
         if (i > istop + 2 && __ddiv_rn(p2, p1) > 1.0) return -1;
-        xk2 = __dsub_rn(
-            __dmul_rn(r2[i - 1],
-                      __dadd_rn(__dsub_rn(__dmul_rn(tm, t), __dmul_rn(xmx, __dadd_rn(__ddiv_rn(c.xkappa, r[i - 1]),
-                                                                                   __dmul_rn(0.75, xmx)))),
-                                __ddiv_rn(xm2[i - 1], tm))),
-            c.xl4);
-        dk2 = __dadd_rn(1.0, __dmul_rn(c.dl2, xk2));
-        if (WRITE) phi[i - 1] = __ddiv_rn(__dmul_rn(p2, sqrt(__dmul_rn(xm, r[i - 1]))), dk2);
+        xk2 = xkN;
+        dk2 = dkN;
+        if (WRITE) phi[i - 1] = dv(__dmul_rn(p2, sqN), dk2);
         reach = i;
         if (fabs(p2) > 10000000000.0) {
             if (WRITE) {
@@ -141,12 +158,45 @@ __device__ int hf_integ(double e, const HfIntegConsts& c, const double* __restri
         }
         p0 = p1;
         p1 = p2;
+        return 2;
+    };
+    int verdict = 2;
+    for (int i = 3; i <= last; i += 2) {
+        double xkA, dkA, sqA, xkB, dkB, sqB, xmA, xmB;
+        coef(i, xkA, dkA, sqA, xmA);
+        coef(min(i + 1, nr), xkB, dkB, sqB, xmB);
+        verdict = step(i, xkA, dkA, sqA);
+        if (verdict != 2) break;
+        if (i + 1 > last) break;
+        verdict = step(i + 1, xkB, dkB, sqB);
+        if (verdict != 2) break;
     }
+    ok = EXACT || trk.ok();
+    if (verdict != 2) return verdict;
     return nn < c.nnideal ? -1 : 0;  // elsolve :763
 }
 
-// grid = number of atoms, block = 1024 threads
-__global__ void __launch_bounds__(1024, 1) hartfock_kernel(const HfProblem* __restrict__ probs) {
+// the sweep with the tracked quotients, repeated with IEEE divisions if an operand left their validity window
+template <bool WRITE>
+__device__ __forceinline__ int hf_integ_any(bool nonrel, double e, const HfIntegConsts& c, const double* __restrict__ v,
+                                            const double* __restrict__ xm1, const double* __restrict__ xm2,
+                                            const double* __restrict__ xkr, const double* __restrict__ r,
+                                            const double* __restrict__ r2, double* phi, int* ev_idx, double* ev_div,
+                                            int& nev, int& reach) {
+    bool ok = true;
+    int nev0 = nev;
+    int ief = nonrel ? hf_integ<WRITE, false, true>(e, c, v, xm1, xm2, xkr, r, r2, phi, ev_idx, ev_div, nev, reach, ok)
+                     : hf_integ<WRITE, false, false>(e, c, v, xm1, xm2, xkr, r, r2, phi, ev_idx, ev_div, nev, reach, ok);
+    if (!ok) {
+        nev = nev0;
+        ief = hf_integ<WRITE, true, false>(e, c, v, xm1, xm2, xkr, r, r2, phi, ev_idx, ev_div, nev, reach, ok);
+    }
+    return ief;
+}
+
+// grid = number of atoms, block = kHfThreads threads (24 warps: one per orbital of all but the heaviest atoms, and 85
+// registers per thread for the two coefficient chains of hf_integ)
+__global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem* __restrict__ probs) {
     const HfProblem& P = probs[blockIdx.x];
     const int nr = P.nr, nel = P.nel, tid = threadIdx.x, nth = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
@@ -172,7 +222,18 @@ __global__ void __launch_bounds__(1024, 1) hartfock_kernel(const HfProblem* __re
     const double dl = P.dl;
     const double ratio = P.ratio, ratio1 = __dsub_rn(1.0, P.ratio);
 
+    const bool nonrel = a2 == 0.0;  // then xm == 1 and tm == 2 exactly in integ
     for (int i = tid; i < nel; i += nth) ev_s[i] = 0.0;
+    // xkappa / r(j) of integ :1077, the same for every energy and every iteration (xkappa as in elsolve :750-752)
+    for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
+        const int o = static_cast<int>(k / nr), j = static_cast<int>(k % nr);
+        const double xj = P.xnj[o];
+        const int l = P.nl[o];
+        double xkappa = -1.0;
+        if (fabs(xj) > static_cast<double>(l) + 0.25) xkappa = static_cast<double>(-l - 1);
+        if (fabs(xj) < static_cast<double>(l) - 0.25) xkappa = static_cast<double>(l);
+        P.xkr[k] = __ddiv_rn(xkappa, r[j]);
+    }
     for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
         P.phe[k] = 0.0;
         P.orb[k] = 0.0;
@@ -212,6 +273,7 @@ __global__ void __launch_bounds__(1024, 1) hartfock_kernel(const HfProblem* __re
             const double* v = P.v + static_cast<long>(o) * nr;
             const double* xm1 = P.xm1 + static_cast<long>(o) * nr;
             const double* xm2 = P.xm2 + static_cast<long>(o) * nr;
+            const double* xkr = P.xkr + static_cast<long>(o) * nr;
             double* phi = P.phe + static_cast<long>(o) * nr;
             double* phi2 = P.phi2 + static_cast<long>(o) * nr;
             const int n = P.no[o], l = P.nl[o];
@@ -262,7 +324,8 @@ __global__ void __launch_bounds__(1024, 1) hartfock_kernel(const HfProblem* __re
                 int nev_dummy = 0, reach_n = 0;
                 int ief_n = 0;
                 if (reachable)
-                    ief_n = hf_integ<false>(e_n, c, v, xm1, xm2, r, r2, nullptr, nullptr, nullptr, nev_dummy, reach_n);
+                    ief_n = hf_integ_any<false>(nonrel, e_n, c, v, xm1, xm2, xkr, r, r2, nullptr, nullptr, nullptr, nev_dummy,
+                                                reach_n);
                 __syncwarp();
                 // walk the tree with the actual verdicts (every lane does the same walk)
                 int d = 0, idx = 0;
@@ -308,7 +371,8 @@ __global__ void __launch_bounds__(1024, 1) hartfock_kernel(const HfProblem* __re
             for (int q = 0; q < nstk; ++q) {
                 if (lane == 0) {
                     int nev = 0, rch = 0;
-                    hf_integ<true>(stk_e_s[warp][q], c, v, xm1, xm2, r, r2, phi, ev_idx_s[warp], ev_div_s[warp], nev, rch);
+                    hf_integ_any<true>(nonrel, stk_e_s[warp][q], c, v, xm1, xm2, xkr, r, r2, phi, ev_idx_s[warp], ev_div_s[warp],
+                                       nev, rch);
                     nev_s[warp] = nev;
                 }
                 __syncwarp();
