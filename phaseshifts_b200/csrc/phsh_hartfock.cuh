@@ -35,6 +35,23 @@ constexpr int kHfMaxNr = 4000;    // nrmax
 constexpr int kHfMaxEvents = 64;  // rescalings of one outward sweep kept for the parallel fix-up
 constexpr int kHfMaxStack = 48;   // sweeps of one bisection whose phi entries survive (see elsolve below)
 constexpr int kHfThreads = 768;
+constexpr int kHfMaxCluster = 8;  // CTAs (SMs) that may share one atom
+
+// ---- thread-block cluster helpers: the CTAs of a cluster work on one atom, exchange through global memory and meet at
+// cluster barriers (release/acquire at cluster scope).  A launch without the cluster attribute is a cluster of one.
+__device__ __forceinline__ unsigned hf_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned hf_cluster_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void hf_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 struct HfTerm {   // one (i, j, la) term of getpot's pair loops, in the reference's order
     int i, j, la, kind;  // kind 0 = direct Coulomb (:473-538), 1 = exchange (:548-613); i, j 0-based
@@ -50,6 +67,10 @@ struct HfProblem {  // one atom; every pointer is a DEVICE pointer into this ato
     const double *r, *dr, *r2, *rpower;  // [nr], rpower [8][nr]
     double *phe, *orb, *v, *xm1, *xm2, *phi2;  // [nel][nr]
     double* xkr;                                 // [nel][nr] xkappa(orbital) / r: the energy-independent quotient of integ
+    // per-orbital scalars and reduction slots shared by the CTAs of the atom's cluster (global memory, cluster barriers)
+    double *evnew, *statusd;  // [kHfMaxOrb] eigenvalue found by elsolve; its status (0 running, 1 converged, 2 mixing too strong)
+    double* red;              // [kHfMaxCluster * 32] per-warp partial sums of the total energy
+    double* scal;             // [2] etot, eerror of the current iteration
     double *contrib;                            // [nterms][2][nr]
     const HfTerm* terms;
     const int* upd_off;   // [nel+1]
@@ -194,19 +215,22 @@ __device__ __forceinline__ int hf_integ_any(bool nonrel, double e, const HfInteg
     return ief;
 }
 
-// grid = number of atoms, block = kHfThreads threads (24 warps: one per orbital of all but the heaviest atoms, and 85
-// registers per thread for the two coefficient chains of hf_integ)
+// grid = number of atoms x cluster size, block = kHfThreads threads (85 registers per thread for the two coefficient
+// chains of hf_integ).  The CTAs of a cluster share one atom: orbitals (elsolve) and pair terms (getpot) are dealt round
+// robin over the CTAs, element-wise loops are split in blocks; everything order-dependent keeps its order, so the
+// results do not depend on the cluster size.
 __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem* __restrict__ probs) {
-    const HfProblem& P = probs[blockIdx.x];
-    const int nr = P.nr, nel = P.nel, tid = threadIdx.x, nth = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    const int crank = static_cast<int>(hf_cluster_rank()), csize = static_cast<int>(hf_cluster_size());
+    const HfProblem& P = probs[blockIdx.x / csize];
+    const int nr = P.nr, nel = P.nel;
+    const int tid_l = threadIdx.x, nth_l = blockDim.x;
+    const int tid = crank * nth_l + tid_l, nth = csize * nth_l;  // blocked over the cluster: element-wise loops
+    const int lane = tid_l & 31, warp = tid_l >> 5, nwarps_l = nth_l >> 5;
+    const int gwarp = tid >> 5, nwarps = nth >> 5;
     const double* __restrict__ r = P.r;
     const double* __restrict__ dr = P.dr;
     const double* __restrict__ r2 = P.r2;
-    __shared__ double ev_s[kHfMaxOrb], evnew_s[kHfMaxOrb], ek_s[kHfMaxOrb], xnorm_s[kHfMaxOrb];
-    __shared__ int status_s[kHfMaxOrb];
-    __shared__ double red_s[32];
-    __shared__ double etot_s, eerror_s;
+    __shared__ double xnorm_s[kHfMaxOrb];
     __shared__ int ev_idx_s[32][kHfMaxEvents];     // per warp: rescale events of a replayed sweep
     __shared__ double ev_div_s[32][kHfMaxEvents];
     __shared__ int nev_s[32];
@@ -223,7 +247,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
     const double ratio = P.ratio, ratio1 = __dsub_rn(1.0, P.ratio);
 
     const bool nonrel = a2 == 0.0;  // then xm == 1 and tm == 2 exactly in integ
-    for (int i = tid; i < nel; i += nth) ev_s[i] = 0.0;
+    for (int i = tid; i < nel; i += nth) P.ev[i] = 0.0;
     // xkappa / r(j) of integ :1077, the same for every energy and every iteration (xkappa as in elsolve :750-752)
     for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
         const int o = static_cast<int>(k / nr), j = static_cast<int>(k % nr);
@@ -238,7 +262,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         P.phe[k] = 0.0;
         P.orb[k] = 0.0;
     }
-    __syncthreads();
+    hf_cluster_sync();
 
     int iter = 0;
     for (;;) {
@@ -257,7 +281,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                 P.xm2[k] = __dadd_rn(__dmul_rn(-a2, ddvdrr), __ddiv_rn(__ddiv_rn(zaa, r2[j - 1]), r[j - 1]));
             }
         }
-        __syncthreads();
+        hf_cluster_sync();
         for (int o = tid; o < nel; o += nth) {
             double* xm1 = P.xm1 + static_cast<long>(o) * nr;
             double* xm2 = P.xm2 + static_cast<long>(o) * nr;
@@ -266,10 +290,10 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
             xm1[0] = __dsub_rn(__dadd_rn(xm1[1], __ddiv_rn(za2, r2[1])), __ddiv_rn(za2, r2[0]));
             xm2[0] = __dadd_rn(__dsub_rn(xm2[1], __ddiv_rn(__ddiv_rn(zaa, r2[1]), r[1])), __ddiv_rn(__ddiv_rn(zaa, r2[0]), r[0]));
         }
-        __syncthreads();
+        hf_cluster_sync();
 
         // ---- elsolve (:742-793): one warp per orbital, five bisection levels per round ---------------------------
-        for (int o = warp; o < nel; o += nwarps) {
+        for (int o = crank + csize * warp; o < nel; o += csize * nwarps_l) {
             const double* v = P.v + static_cast<long>(o) * nr;
             const double* xm1 = P.xm1 + static_cast<long>(o) * nr;
             const double* xm2 = P.xm2 + static_cast<long>(o) * nr;
@@ -388,8 +412,8 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                 __syncwarp();
             }
             if (lane == 0) {
-                evnew_s[o] = e_last;
-                status_s[o] = status;
+                P.evnew[o] = e_last;
+                P.statusd[o] = static_cast<double>(status);
             }
             // entries no sweep of this bisection reached keep the previous iteration's values, as in the Fortran
             if (status == 1) {
@@ -449,26 +473,26 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                                                    3.0));
                     ll = 6 - ll;
                 }
-                ek_s[o] = ekk;
+                P.ek[o] = ekk;
             }
         }
-        __syncthreads();
+        hf_cluster_sync();
         if (tid == 0) {
             double eerror = 0.0, etot = 0.0;
             for (int i = 0; i < nel; ++i) {
-                const double dlt = fabs(__dsub_rn(ev_s[i], evnew_s[i]));
+                const double dlt = fabs(__dsub_rn(P.ev[i], P.evnew[i]));
                 if (dlt > eerror) eerror = dlt;
-                ev_s[i] = evnew_s[i];
-                etot = __dadd_rn(etot, __dmul_rn(ek_s[i], P.occ[i]));
+                P.ev[i] = P.evnew[i];
+                etot = __dadd_rn(etot, __dmul_rn(P.ek[i], P.occ[i]));
             }
-            eerror_s = eerror;
-            etot_s = etot;
+            P.scal[1] = eerror;
+            P.scal[0] = etot;
         }
         // ---- getpot (:443-739) -----------------------------------------------------------------------------------
         for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) P.orb[k] = __dmul_rn(ratio1, P.orb[k]);
         double etot_part = 0.0;
         const double xnum2 = __dmul_rn(P.xnum, P.xnum);
-        for (int t = tid; t < P.nterms; t += nth) {
+        for (int t = tid_l * csize + crank; t < P.nterms; t += nth) {
             const HfTerm T = P.terms[t];
             const double* __restrict__ pi = P.phe + static_cast<long>(T.i) * nr;
             const double* __restrict__ pj = P.phe + static_cast<long>(T.j) * nr;
@@ -560,7 +584,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                 }
             }
         }
-        __syncthreads();
+        hf_cluster_sync();
         // add the contributions in the order of the reference's pair loops: one thread per (orbital, r)
         for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
             const int o = static_cast<int>(k / nr), kk = static_cast<int>(k % nr);
@@ -573,15 +597,15 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         {
             double s = etot_part;
             for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-            if (lane == 0) red_s[warp] = s;
+            if (lane == 0) P.red[gwarp] = s;
         }
-        __syncthreads();
+        hf_cluster_sync();
         if (tid == 0) {
-            double s = etot_s;
-            for (int w = 0; w < nwarps; ++w) s += red_s[w];
-            etot_s = s;
+            double s = P.scal[0];
+            for (int w = 0; w < nwarps; ++w) s += P.red[w];
+            P.scal[0] = s;
         }
-        __syncthreads();
+        hf_cluster_sync();
         // local exchange / correlation (:617-660) -- alfa != 0 only
         if (fabs(P.alfa) >= 0.001) {
             double fx, fc;
@@ -649,16 +673,16 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                 }
             }
             for (int off = 16; off > 0; off >>= 1) epart += __shfl_down_sync(0xffffffffu, epart, off);
-            __syncthreads();
-            if (lane == 0) red_s[warp] = epart;
-            __syncthreads();
+            hf_cluster_sync();
+            if (lane == 0) P.red[gwarp] = epart;
+            hf_cluster_sync();
             if (tid == 0) {
-                double s = etot_s;
-                for (int w = 0; w < nwarps; ++w) s += red_s[w];
-                etot_s = s;
+                double s = P.scal[0];
+                for (int w = 0; w < nwarps; ++w) s += P.red[w];
+                P.scal[0] = s;
             }
         }
-        __syncthreads();
+        hf_cluster_sync();
         // shell averaging (:662-736), iuflag = 1: same n, l, spin; 2: same n, l
         if (P.iuflag != 0) {
             for (int i = tid; i < nr; i += nth) {
@@ -686,19 +710,19 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                     jj = ii + 1;
                 }
             }
-            __syncthreads();
+            hf_cluster_sync();
         }
         // ---- convergence (abinitio :338-349) -----------------------------------------------------------------------
-        const double eerr = __ddiv_rn(__dmul_rn(eerror_s, ratio1), ratio);
+        const double eerr = __ddiv_rn(__dmul_rn(P.scal[1], ratio1), ratio);
         if (tid == 0 && iter < P.max_iter) {
             P.history[2 * iter] = eerr;
-            P.history[2 * iter + 1] = etot_s;
+            P.history[2 * iter + 1] = P.scal[0];
         }
         ++iter;
         if (!(eerr > P.etol) || iter >= P.max_iter) break;
-        __syncthreads();
+        hf_cluster_sync();
     }
-    __syncthreads();
+    hf_cluster_sync();
     // charge density of hfdisk (:1889-1896) and the bookkeeping
     for (int i = tid; i < nr; i += nth) {
         double s = 0.0;
@@ -708,17 +732,13 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         }
         P.rho[i] = s;
     }
-    for (int i = tid; i < nel; i += nth) {
-        P.ev[i] = ev_s[i];
-        P.ek[i] = ek_s[i];
-    }
     if (tid == 0) {
         int mixing = 0;
-        for (int i = 0; i < nel; ++i) mixing |= (status_s[i] == 2);
-        P.info[0] = etot_s;
+        for (int i = 0; i < nel; ++i) mixing |= (P.statusd[i] == 2.0);
+        P.info[0] = P.scal[0];
         P.info[1] = static_cast<double>(iter);
         P.info[2] = static_cast<double>(mixing);
-        P.info[3] = __ddiv_rn(__dmul_rn(eerror_s, ratio1), ratio);
+        P.info[3] = __ddiv_rn(__dmul_rn(P.scal[1], ratio1), ratio);
     }
 }
 

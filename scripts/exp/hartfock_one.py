@@ -1,8 +1,16 @@
-"""One hartfock run of the Re fixture through the host API (scratch; the command profiled by ncu)."""
+"""Hartfock timing through the host API (scratch; the command profiled by ncu): the Re fixture file, then batches of
+carbon atoms; PHSH_B200_HARTFOCK_CLUSTER = 1 | 2 | 4 | 8 overrides the cluster size."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from phaseshifts_b200 import api
 os.chdir("/tmp")
 src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "tests", "golden", "Re0001", "atorb_Re")
-for _ in range(2):
+for _ in range(3):
     t0 = time.perf_counter(); api.hartfock_file(src); print("Re file: %.1f ms" % ((time.perf_counter() - t0) * 1e3))
+if len(sys.argv) > 1:
+    C_ORB = [(1, 0, 0, -0.5, 1, 2.0), (2, 0, 0, -0.5, 1, 2.0), (2, 1, 1, -0.5, 1, 2.0 / 3.0), (2, 1, 1, -1.5, 1, 4.0 / 3.0)]
+    for n in (1, 18, 37, 74, 148):
+        atoms = [dict(z=6, nr=1000, rel=1.0, orbitals=C_ORB)] * n
+        api.hartfock_batch(atoms[:1])
+        t0 = time.perf_counter(); r = api.hartfock_batch(atoms); dt = time.perf_counter() - t0
+        print("carbon x%d: %.1f ms, %d iterations" % (n, dt * 1e3, r[0]["scf_iterations"]))

@@ -90,6 +90,21 @@ def test_batch_of_several_atoms_in_one_launch(hio):
         assert abs(float((g["rho"] * r * (np.sqrt(x) - 1 / np.sqrt(x))).sum()) - sum(o[5] for o in a["orbitals"])) < 1e-8
 
 
+def test_results_do_not_depend_on_the_cluster_size(hio, monkeypatch):
+    """One atom may be shared by the 1, 2, 4 or 8 CTAs of a thread-block cluster (orbitals and pair terms dealt round robin,
+    exchange through global memory at cluster barriers): eigenvalues, charge density and iteration count must be the same
+    bits whatever the size, and equal to the oracle's."""
+    from phaseshifts_b200 import api
+    atoms = [dict(z=6, nr=1000, rel=1.0, orbitals=C_ORB), dict(z=3, nr=800, rel=0.0, orbitals=[(1, 0, 0, -0.5, 1, 2.0), (2, 0, 0, -0.5, 1, 1.0)])]
+    want = [_oracle(hio, a["z"], a["nr"], a["rel"], 0.0, 0, a["orbitals"]) for a in atoms]
+    for c in (1, 2, 4, 8):
+        monkeypatch.setenv("PHSH_B200_HARTFOCK_CLUSTER", str(c))
+        got = api.hartfock_batch(atoms)
+        for g, w in zip(got, want):
+            assert g["scf_iterations"] == w["scf_iterations"], c
+            assert np.array_equal(g["rho"], w["rho"]) and np.array_equal(g["ev"][: len(w["ev"])], w["ev"]), c
+
+
 def test_shell_averaging_and_local_exchange_modes(hio):
     from phaseshifts_b200 import api
     for iuflag in (1, 2):
