@@ -186,16 +186,56 @@ __device__ __noinline__ int hf_integ(double e, const HfIntegConsts& c, const dou
         return 2;
     };
     int verdict = 2;
-    for (int i = 3; i <= last; i += 2) {
-        double xkA, dkA, sqA, xkB, dkB, sqB, xmA, xmB;
-        coef(i, xkA, dkA, sqA, xmA);
-        coef(min(i + 1, nr), xkB, dkB, sqB, xmB);
-        verdict = step(i, xkA, dkA, sqA);
-        if (verdict != 2) break;
-        if (i + 1 > last) break;
-        verdict = step(i + 1, xkB, dkB, sqB);
-        if (verdict != 2) break;
+    int i = 3;
+    if (!WRITE) {
+        // Speculative sweeps (the bulk of the work) up to the turning point: the arithmetic of two steps and of their
+        // coefficients forms ONE basic block -- the node count and the exits are evaluated after it, and the rare rescaling
+        // (|p2| > 1e10 changes p0, p1 before the next step) sends the pair through the step-by-step code below instead.
+        const int pair_end = min(istop + 2, last);  // no blow-up test up to here (:1070-1105)
+        for (; i + 1 <= pair_end; i += 2) {
+            double xkA, dkA, sqA, xkB, dkB, sqB, xmA, xmB;
+            coef(i, xkA, dkA, sqA, xmA);
+            coef(i + 1, xkB, dkB, sqB, xmB);
+            const double p2a = __dsub_rn(dv(__dmul_rn(__dsub_rn(2.0, __dmul_rn(c.dl5, xk2)), p1), dk2), p0);
+            const double p2b = __dsub_rn(dv(__dmul_rn(__dsub_rn(2.0, __dmul_rn(c.dl5, xkA)), p2a), dkA), p1);
+            const bool big = fabs(p2a) > 10000000000.0 || fabs(p2b) > 10000000000.0;
+            const int na = __dmul_rn(p2a, p1) < 0.0 ? 1 : 0, nb = __dmul_rn(p2b, p2a) < 0.0 ? 1 : 0;
+            if (big) {
+                verdict = step(i, xkA, dkA, sqA);
+                if (verdict != 2) break;
+                verdict = step(i + 1, xkB, dkB, sqB);
+                if (verdict != 2) break;
+                continue;
+            }
+            if (na && nn + 1 > c.nnideal) {
+                reach = i;
+                verdict = 1;
+                break;
+            }
+            if (nb && nn + na + 1 > c.nnideal) {
+                reach = i + 1;
+                verdict = 1;
+                break;
+            }
+            nn = nn + na + nb;
+            reach = i + 1;
+            p0 = p2a;
+            p1 = p2b;
+            xk2 = xkB;
+            dk2 = dkB;
+        }
     }
+    if (verdict == 2)
+        for (; i <= last; i += 2) {
+            double xkA, dkA, sqA, xkB, dkB, sqB, xmA, xmB;
+            coef(i, xkA, dkA, sqA, xmA);
+            coef(min(i + 1, nr), xkB, dkB, sqB, xmB);
+            verdict = step(i, xkA, dkA, sqA);
+            if (verdict != 2) break;
+            if (i + 1 > last) break;
+            verdict = step(i + 1, xkB, dkB, sqB);
+            if (verdict != 2) break;
+        }
     ok = EXACT || trk.ok();
     if (verdict != 2) return verdict;
     return nn < c.nnideal ? -1 : 0;  // elsolve :763
