@@ -595,6 +595,7 @@ def hartfock_batch(atoms, *, history_cap=64, asbuilt=False, device=0):
         it = int(info[k, 1])
         out.append(dict(rho=rho[k, : int(a["nr"])].copy(), ev=ev[k, : keep[k].shape[0]].copy(), etot=float(info[k, 0]),
                         scf_iterations=it, mixing_too_strong=bool(info[k, 2]), rmin=float(info[k, 4]), rmax=float(info[k, 5]),
+                        elsolve_ms=float(info[k, 6]) * 1e-6, getpot_ms=float(info[k, 7]) * 1e-6,
                         history=hist[k, : 2 * min(it, history_cap)].reshape(-1, 2).copy()))
     return out
 

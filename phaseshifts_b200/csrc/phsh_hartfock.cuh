@@ -308,6 +308,13 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
     }
     hf_cluster_sync();
 
+    // wall time of the phases as thread 0 of the cluster sees them (ns, %globaltimer): info[6] elsolve, info[7] getpot
+    auto now_ns = [] {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    };
+    unsigned long long t_elsolve = 0, t_getpot = 0, t_mark = 0;
     int iter = 0;
     for (;;) {
         // ---- setqmm (:844-931), njrc = 0: v, xm1, xm2 of every orbital ------------------------------------------
@@ -337,6 +344,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         hf_cluster_sync();
 
         // ---- elsolve (:742-793): one warp per orbital, five bisection levels per round ---------------------------
+        if (tid == 0) t_mark = now_ns();
         for (int o = crank + csize * warp; o < nel; o += csize * nwarps_l) {
             const double* v = P.v + static_cast<long>(o) * nr;
             const double* xm1 = P.xm1 + static_cast<long>(o) * nr;
@@ -522,6 +530,11 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         }
         hf_cluster_sync();
         if (tid == 0) {
+            const unsigned long long t = now_ns();
+            t_elsolve += t - t_mark;
+            t_mark = t;
+        }
+        if (tid == 0) {
             double eerror = 0.0, etot = 0.0;
             for (int i = 0; i < nel; ++i) {
                 const double dlt = fabs(__dsub_rn(P.ev[i], P.evnew[i]));
@@ -653,6 +666,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
             if (!(P.rpinv_ok && scan_term(T, t, std::true_type()))) scan_term(T, t, std::false_type());
         }
         hf_cluster_sync();
+        if (tid == 0) t_getpot += now_ns() - t_mark;
         // add the contributions in the order of the reference's pair loops: one thread per (orbital, r)
         for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
             const int o = static_cast<int>(k / nr), kk = static_cast<int>(k % nr);
@@ -807,6 +821,8 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         P.info[1] = static_cast<double>(iter);
         P.info[2] = static_cast<double>(mixing);
         P.info[3] = __ddiv_rn(__dmul_rn(P.scal[1], ratio1), ratio);
+        P.info[6] = static_cast<double>(t_elsolve);
+        P.info[7] = static_cast<double>(t_getpot);
     }
 }
 

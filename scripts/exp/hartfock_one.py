@@ -7,6 +7,12 @@ os.chdir("/tmp")
 src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "tests", "golden", "Re0001", "atorb_Re")
 for _ in range(3):
     t0 = time.perf_counter(); api.hartfock_file(src); print("Re file: %.1f ms" % ((time.perf_counter() - t0) * 1e3))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+from oracle import hartfock_io
+cmds = dict(hartfock_io.parse_atorb(src))
+a = cmds["a"]
+t0 = time.perf_counter(); r = api.hartfock_batch([dict(z=cmds["i"][0], nr=cmds["i"][1], rel=cmds["d"], orbitals=a["orbitals"], ratio=a["ratio"], etol=a["etol"], xnum=a["xnum"])])[0]
+print("Re batch API: %.1f ms wall, elsolve %.1f ms, getpot scans %.1f ms, %d iterations" % ((time.perf_counter() - t0) * 1e3, r["elsolve_ms"], r["getpot_ms"], r["scf_iterations"]))
 if len(sys.argv) > 1:
     C_ORB = [(1, 0, 0, -0.5, 1, 2.0), (2, 0, 0, -0.5, 1, 2.0), (2, 1, 1, -0.5, 1, 2.0 / 3.0), (2, 1, 1, -1.5, 1, 4.0 / 3.0)]
     for n in (1, 18, 37, 74, 148):
