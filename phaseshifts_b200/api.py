@@ -560,7 +560,7 @@ def cavpot_file(mtz_string, slab_flag, atomic_file, cluster_file, mufftin_file, 
 
 
 def selftest_cavpot(n=1 << 22, seed=1, device=0):
-    """Mismatches (must be 0) of cavpot_kernel's table-driven division and mesh-index look-up against the IEEE division
+    """Mismatches (must be 0) of the cavpot kernels' table-driven divisions, square root and mesh-index look-up against the IEEE division
     and the threshold table, on ``n`` pseudo-random operands plus the doubles around every threshold."""
     bad = C.c_ulonglong(0)
     _lib.check(_lib.load().phsh_b200_selftest_cavpot(int(n), int(seed), C.byref(bad), int(device)))

@@ -1,7 +1,7 @@
 """The drop-in boundary on the REAL device: the unmodified reference package (staged by ``baseline/make_ref.py`` under
 the git-ignored ``baseline/_ref/``, or a checkout named by ``PHASESHIFTS_REFERENCE``) drives ``libphsh_b200.so`` through
 its own plugin registry, ``phsh.Wrapper`` and CLI -- nothing of ``phaseshifts_b200.api`` is monkeypatched, so
-``rel_integrate_kernel`` and ``cavpot_kernel`` are what produce the ``.phs`` files compared with the reference's golden
+``rel_integrate_kernel`` and the ``cavpot_*`` kernels are what produce the ``.phs`` files compared with the reference's golden
 ``leedph_Re.d`` (reference call sites: ``phsh.py:311-345, 365-482, 811-868``; ``backends.py:177-203``)."""
 import os
 import shutil
@@ -77,7 +77,7 @@ def test_wrapper_with_replayed_mufftin_on_device(wired, monkeypatch):
 
 
 def test_wrapper_nothing_replayed_cavpot_and_phsh_rel_on_device(wired):
-    """cluster.i + at_Re.i -> cavpot_kernel -> rel_integrate_kernel -> the reference's Conphas -> .phs, all through the
+    """cluster.i + at_Re.i -> cavpot_* kernels -> rel_integrate_kernel -> the reference's Conphas -> .phs, all through the
     unmodified Wrapper; within 2.5e-4 of the golden leedph (REAL*4 noise of the fixture's potentials)."""
     import phaseshifts.backends as B
     _, work = wired
@@ -114,7 +114,7 @@ def test_cli_on_device_with_energy_range(wired):
 
 def test_cold_start_cluster_files_only_hartfock_cavpot_phsh_rel_on_device(wired, tmp_path):
     """Nothing pre-placed: the unmodified Wrapper finds no at_Re.i, generates the atorb input itself (atorb.py gen_input) and
-    calls `libphsh.hartfock` -> hartfock_kernel, then `libphsh.cavpot` -> cavpot_kernel, `libphsh.phsh_rel` ->
+    calls `libphsh.hartfock` -> hartfock_kernel, then `libphsh.cavpot` -> the cavpot_* kernels, `libphsh.phsh_rel` ->
     rel_integrate_kernel and its own Conphas.  The generated input is not the fixture's atorb_Re (5d occupations 2 + 3
     instead of 1.875 + 3.125, another orbital order), so the at_Re.i written on the way is checked byte for byte against
     the CPU oracle run on the very same generated input, and the .phs files against the golden leedph at the accuracy
