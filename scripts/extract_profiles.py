@@ -119,7 +119,7 @@ summary("cav", "cav_ps", "cav_ps_kernel<4,5>", "C2 potentials tiled to 4096 x 19
         NCU % ("cav_ps_kernel -s 1", "python scripts/exp/cav_one_launch.py"))
 summary("wil", "wil_integrate", "wil_integrate_kernel", "C5 potentials, 16384 x 500 energies x 13 l",
         NCU % ("wil_integrate -s 1", "python scripts/exp/wil_time.py"))
-for k in ("prep", "sumax", "classify", "mtz_sum", "finish"):
+for k in ("prep", "sumax", "classify", "mtz_sum", "finish"):  # finish: the light instantiation (third launch of the command)
     summary("cavpot_" + k, "cavpot_" + k, "cavpot_%s_kernel" % k, "C6: 4096 perturbed Re(0001) bulk cells, 2 atom types, NH=10, NFORM=2",
             NCU % ("cavpot_%s -s 1" % k, "python scripts/exp/cavpot_dev_time.py 4096 2"))
 
