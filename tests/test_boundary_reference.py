@@ -4,7 +4,12 @@ registry and the CLI), as far as it can be exercised in the build container: the
 (``api.phsh_rel_file``) is replaced by the oracle's file layer -- test infrastructure standing in for the
 device, exactly like the reference's own tests monkeypatch ``cavpot`` (tests/test_phsh_helpers.py:35-50).
 Everything else -- stand-in module seeding, registry, Wrapper, split_phasout, Conphas, .phs writing -- is
-the reference's own code.  Skipped where the reference is not importable."""
+the reference's own code.  Skipped where the reference is not importable.
+
+What this file checks is the HOST wiring (registry, stand-in module, file contracts) against the reference's own code.  The
+same boundary with the real device and no substitution -- unmodified Wrapper / registry / CLI -> hartfock, cavpot and
+rel kernels on the B200 -> .phs against the golden leedph_Re.d -- is tests/test_boundary_gpu.py (``-m gpu``), which runs on the
+GPU box from the staged copy of the reference's Python package (baseline/make_ref.py)."""
 import os
 import shutil
 import sys
