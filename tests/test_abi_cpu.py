@@ -182,3 +182,44 @@ def test_cavpot_mesh_helpers():
     lo, wa = api.cavpot_mesh(0), api.cavpot_mesh(2)
     assert lo.shape == (250,) and wa.shape == (421,) and abs(wa[-1] - 60.0) < 1e-9 and abs(lo[0] - np.exp(-8.8)) < 1e-10
     assert np.allclose(np.diff(np.log(wa)), 0.03125, atol=1e-12) and np.allclose(np.diff(np.log(lo)), 0.05, atol=1e-6)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The ctypes mirrors in _lib.py against the C compiler's view of include/phsh_b200.h: size and every field offset of
+    every struct that crosses the ABI (a field added to one side only would silently shift the rest)."""
+    import ctypes as C
+    import re
+    import shutil
+    import subprocess
+    from phaseshifts_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    pairs = {"phsh_b200_rel_opts": _lib.RelOpts, "phsh_b200_file_opts": _lib.FileOpts, "phsh_b200_conphas_opts": _lib.ConphasOpts,
+             "phsh_b200_cavpot_batch": _lib.CavpotBatch, "phsh_b200_cavpot_result": _lib.CavpotResult,
+             "phsh_b200_hartfock_atom": _lib.HartfockAtom}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "phsh_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for ln in out.splitlines():
+        cname, what, val = ln.split()
+        cls = pairs[cname]
+        if what == "size":
+            assert C.sizeof(cls) == int(val), (cname, C.sizeof(cls), val)
+        else:
+            assert getattr(cls, what).offset == int(val), (cname, what, getattr(cls, what).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
+    # and no struct of the header is missing from the list
+    hdr = open(os.path.join(inc, "phsh_b200.h")).read()
+    assert set(re.findall(r"typedef struct (phsh_b200_\w+)", hdr)) == set(pairs)
