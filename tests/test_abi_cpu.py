@@ -223,3 +223,29 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     # and no struct of the header is missing from the list
     hdr = open(os.path.join(inc, "phsh_b200.h")).read()
     assert set(re.findall(r"typedef struct (phsh_b200_\w+)", hdr)) == set(pairs)
+
+
+def test_hartfock_file_reports_bad_input_before_it_needs_a_device(lib, tmp_path, monkeypatch):
+    """The command stream of an atorb file is checked as it is read: a missing file, a command of the pseudopotential
+    generator or a malformed record is refused without a GPU; only a well-formed 'a' command asks for the device."""
+    from phaseshifts_b200 import api, _lib
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(_lib.PhshB200Error) as e:
+        api.hartfock_file("nowhere")
+    assert e.value.code == _lib.EIO
+    (tmp_path / "pseudo").write_text("i\n75 1000\np\n")
+    with pytest.raises(_lib.PhshB200Error) as e:
+        api.hartfock_file("pseudo")
+    assert e.value.code == _lib.EINVAL and "pseudopotential" in str(e.value)
+    (tmp_path / "short").write_text("i\n75\n")
+    with pytest.raises(_lib.PhshB200Error) as e:
+        api.hartfock_file("short")
+    assert e.value.code == _lib.EIO
+    (tmp_path / "frozen").write_text("i\n3 600\na\n1 2 0.5 0.0005 100\n")
+    with pytest.raises(_lib.PhshB200Error) as e:
+        api.hartfock_file("frozen")
+    assert e.value.code == _lib.EINVAL and "frozen core" in str(e.value)
+    if _lib.device_count() == 0:
+        with pytest.raises(_lib.PhshB200Error) as e:
+            api.hartfock_file(os.path.join(ROOT, "tests", "golden", "Re0001", "atorb_Re"))
+        assert e.value.code == _lib.ENODEV
