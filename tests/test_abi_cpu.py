@@ -245,6 +245,12 @@ def test_hartfock_file_reports_bad_input_before_it_needs_a_device(lib, tmp_path,
     with pytest.raises(_lib.PhshB200Error) as e:
         api.hartfock_file("frozen")
     assert e.value.code == _lib.EINVAL and "frozen core" in str(e.value)
+    with pytest.raises(_lib.PhshB200Error) as e:
+        api.hartfock_batch([dict(z=6, nr=2, rel=1.0, orbitals=[(1, 0, 0, -0.5, 1, 2.0)])])
+    assert e.value.code == _lib.EINVAL
+    with pytest.raises(_lib.PhshB200Error) as e:
+        api.hartfock_batch([dict(z=200, nr=800, rel=1.0, orbitals=[(1, 0, 0, -0.5, 1, 2.0)])])
+    assert e.value.code == _lib.EINVAL and "TOO BIG" in str(e.value)
     if _lib.device_count() == 0:
         with pytest.raises(_lib.PhshB200Error) as e:
             api.hartfock_file(os.path.join(ROOT, "tests", "golden", "Re0001", "atorb_Re"))
