@@ -18,6 +18,9 @@ __global__ void k(double* out, int iters, double a0, double b0) {
                 if (MODE == 3) x[i] = __dmul_rn(x[i], a[i]);
                 if (MODE == 4) x[i] = __dadd_rn(x[i], b[i]);
                 if (MODE == 5) { x[i] = __dmul_rn(x[i], a[i]); x[i] = __dadd_rn(x[i], b[i]); }  // dependent mul+add pairs
+                if (MODE == 6) x[i] = __fma_rn(x[i], a[i], x[i]);              // two distinct registers
+                if (MODE == 7) x[i] = __fma_rn(x[i], a[i], b0);                // two registers and a constant
+                if (MODE == 8) x[i] = __fma_rn(a[i], b[i], x[i]);              // three distinct, accumulator form
             }
     }
     double s = 0;
@@ -55,6 +58,9 @@ int main() {
     run<3, 8>("DMUL two registers", 256, 4, sms, d, mhz);
     run<4, 8>("DADD two registers", 256, 4, sms, d, mhz);
     run<5, 8>("DMUL then dependent DADD", 256, 4, sms, d, mhz);
+    run<6, 8>("DFMA two distinct registers", 256, 4, sms, d, mhz);
+    run<7, 8>("DFMA two registers + constant", 256, 4, sms, d, mhz);
+    run<8, 8>("DFMA three distinct, accumulator", 256, 4, sms, d, mhz);
     run<1, 4>("DFMA three distinct registers", 128, 6, sms, d, mhz);
     run<1, 2>("DFMA three distinct registers", 128, 6, sms, d, mhz);
     run<1, 1>("DFMA three distinct, 1 chain", 128, 6, sms, d, mhz);
