@@ -38,6 +38,11 @@ constexpr int kHfMaxEvents = 64;  // rescalings of one outward sweep kept for th
 constexpr int kHfMaxStack = 48;   // sweeps of one bisection whose phi entries survive (see elsolve below)
 constexpr int kHfThreads = 768;
 constexpr int kHfMaxCluster = 8;  // CTAs (SMs) that may share one atom
+constexpr int kHfTeamMaxW = 8;    // warps of one orbital's team when the CTA has warps to spare (see hf_team_round)
+constexpr int kHfEntry = 96;      // doubles of one tabulated mesh point: A, y, dk of 32 energies
+// dynamic shared memory of hartfock_kernel: the coefficient tiles of the teams (2 buffers x 4 mesh points per producer
+// warp; three producers in each of six teams or six in each of three)
+constexpr size_t kHfDynSmem = static_cast<size_t>(kHfThreads / 32 / 4) * 2 * 4 * 3 * kHfEntry * sizeof(double);
 
 // ---- thread-block cluster helpers: the CTAs of a cluster work on one atom, exchange through global memory and meet at
 // cluster barriers (release/acquire at cluster scope).  A launch without the cluster attribute is a cluster of one.
@@ -55,6 +60,16 @@ __device__ __forceinline__ void hf_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+#ifdef PHSH_HF_PROFILE
+__device__ unsigned long long hf_prof_g[16];
+#define HF_PROF_T0() const long long prof_t0 = clock64()
+#define HF_PROF_ADD(k) if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[k] += static_cast<unsigned long long>(clock64() - prof_t0)
+#endif
+// named barrier of one team of warps (id 1..15; bar.sync orders the shared-memory traffic of the participants)
+__device__ __forceinline__ void hf_team_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 struct HfTerm {   // one (i, j, la) term of getpot's pair loops, in the reference's order
     int i, j, la, kind;  // kind 0 = direct Coulomb (:473-538), 1 = exchange (:548-613); i, j 0-based
     double ri, rj, rc;
@@ -62,6 +77,7 @@ struct HfTerm {   // one (i, j, la) term of getpot's pair loops, in the referenc
 
 struct HfProblem {  // one atom; every pointer is a DEVICE pointer into this atom's workspace
     int nr, nel, nterms, iuflag, max_iter, asbuilt;
+    int team_mode;  // 0: teams where the CTA has warps to spare; 1: never; 2: always take the exact repeat (both testing aids)
     double z, rel, alfa, ratio, etol, xnum, dl;
     double pw12[kHfMaxOrb];  // (r(2)/r(1))**(ss-1/2) of integ :1052 (ss = l+1 without relativity, else sqrt(1-(z alpha)^2))
     int no[kHfMaxOrb], nl[kHfMaxOrb], is[kHfMaxOrb];
@@ -71,6 +87,7 @@ struct HfProblem {  // one atom; every pointer is a DEVICE pointer into this ato
     int rpinv_ok;                        // 0: some rpower has an all-ones significand (cp_div's exceptional case): IEEE divisions
     double *phe, *orb, *v, *xm1, *xm2, *phi2;  // [nel][nr]
     double* xkr;                                 // [nel][nr] xkappa(orbital) / r: the energy-independent quotient of integ
+    double* vsm;                                 // [nel][nr] vsm(j) = min v(j .. nr-1): integ's turning point by bisection
     // per-orbital scalars and reduction slots shared by the CTAs of the atom's cluster (global memory, cluster barriers)
     double *evnew, *statusd;  // [kHfMaxOrb] eigenvalue found by elsolve; its status (0 running, 1 converged, 2 mixing too strong)
     double* red;              // [kHfMaxCluster * 32] per-warp partial sums of the total energy
@@ -86,12 +103,30 @@ struct HfProblem {  // one atom; every pointer is a DEVICE pointer into this ato
 
 struct HfIntegConsts {
     double dl2, dl5, a2, xl4, xlp, z, pw12, xkappa;
+    const double* vsm;  // suffix minima of this orbital's v
     int nnideal, nr;
 };
 
+// classical turning point of integ (:1059-1068): the LAST j in 2 .. nr-1 with e > v(j), 0 if there is none.  The Fortran
+// scans downwards from nr-1; with the suffix minima vsm(j) = min v(j .. nr-1) the condition "some j' >= j has e > v(j')" is
+// e > vsm(j), true exactly for j <= that last j: ten bisection steps instead of up to nr loads
+__device__ __forceinline__ int hf_turning_point(double e, const double* __restrict__ vsm, int nr) {
+    if (nr < 3 || !(e > vsm[1])) return 0;
+    int lo = 2, hi = nr;  // e > vsm(lo); not so at hi (hi = nr stands for "beyond the range")
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (e > vsm[mid - 1])
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
 // integ (libphsh.f:992-1165) with istop = 0 on entry.  Returns the verdict (ief after elsolve's node-count override,
-// :763) and, in `reach`, the last index of phi the sweep assigns.  WRITE = true also stores phi, with the |p2| > 1e10
-// rescalings recorded so that the warp can apply them in parallel afterwards.
+// :763) and, in `reach`, the last index of phi the sweep assigns.  WRITE = true also stores phi(wlo+1 .. reach) -- the
+// entries no later sweep of the bisection overwrites -- with the |p2| > 1e10 rescalings recorded so that the warp can
+// apply them in parallel afterwards.
 //
 // The sweep is a 1000-step recurrence per lane and the whole atomic step is bound by its latency, so it is arranged for
 // instruction-level parallelism without changing one rounding:
@@ -107,8 +142,8 @@ template <bool WRITE, bool EXACT, bool NONREL>
 __device__ __noinline__ int hf_integ(double e, const HfIntegConsts& c, const double* __restrict__ v,
                                      const double* __restrict__ xm1, const double* __restrict__ xm2,
                                      const double* __restrict__ xkr, const double* __restrict__ r,
-                                     const double* __restrict__ r2, double* phi, int* ev_idx, double* ev_div, int& nev,
-                                     int& reach, bool& ok) {
+                                     const double* __restrict__ r2, double* phi, int wlo, int* ev_idx, double* ev_div,
+                                     int& nev, int& reach, bool& ok) {
     const int nr = c.nr;
     DivTrack trk;
     trk.reset();
@@ -136,19 +171,13 @@ __device__ __noinline__ int hf_integ(double e, const HfIntegConsts& c, const dou
     double xk0, dk0, sq0, xm0;
     coef(1, xk0, dk0, sq0, xm0);
     double p0 = dk0;
-    if (WRITE) phi[0] = __ddiv_rn(__dmul_rn(p0, sq0), dk0);
+    if (WRITE && wlo < 1) phi[0] = __ddiv_rn(__dmul_rn(p0, sq0), dk0);
     double xk2, dk2, sq2, xm;
     coef(2, xk2, dk2, sq2, xm);
     double p1 = __dmul_rn(
         __dmul_rn(dk2, __dsub_rn(c.pw12, __ddiv_rn(__dmul_rn(__dsub_rn(r[1], r[0]), c.z), c.xlp))), sqrt(__ddiv_rn(xm0, xm)));
-    if (WRITE) phi[1] = __ddiv_rn(__dmul_rn(p1, sq2), dk2);
-    // classical turning point (:1059-1068)
-    int istop = 0;
-    for (int j = nr - 1; j >= 2; --j)
-        if (e > v[j - 1]) {
-            istop = j;
-            break;
-        }
+    if (WRITE && wlo < 2) phi[1] = __ddiv_rn(__dmul_rn(p1, sq2), dk2);
+    const int istop = hf_turning_point(e, c.vsm, nr);  // classical turning point (:1059-1068)
     reach = 2;
     ok = true;
     if (istop == 0) return -1;
@@ -161,7 +190,7 @@ __device__ __noinline__ int hf_integ(double e, const HfIntegConsts& c, const dou
         if (i > istop + 2 && __ddiv_rn(p2, p1) > 1.0) return -1;
         xk2 = xkN;
         dk2 = dkN;
-        if (WRITE) phi[i - 1] = dv(__dmul_rn(p2, sqN), dk2);
+        if (WRITE && i > wlo) phi[i - 1] = dv(__dmul_rn(p2, sqN), dk2);
         reach = i;
         if (fabs(p2) > 10000000000.0) {
             if (WRITE) {
@@ -170,7 +199,7 @@ __device__ __noinline__ int hf_integ(double e, const HfIntegConsts& c, const dou
                     ev_div[nev] = p2;
                     ++nev;
                 } else {  // list full (never for a physical atom): divide at once like the Fortran
-                    for (int j = 1; j <= i; ++j) phi[j - 1] = __ddiv_rn(phi[j - 1], p2);
+                    for (int j = wlo + 1; j <= i; ++j) phi[j - 1] = __ddiv_rn(phi[j - 1], p2);
                 }
             }
             p0 = __ddiv_rn(p0, p2);
@@ -246,17 +275,293 @@ template <bool WRITE>
 __device__ __forceinline__ int hf_integ_any(bool nonrel, double e, const HfIntegConsts& c, const double* __restrict__ v,
                                             const double* __restrict__ xm1, const double* __restrict__ xm2,
                                             const double* __restrict__ xkr, const double* __restrict__ r,
-                                            const double* __restrict__ r2, double* phi, int* ev_idx, double* ev_div,
-                                            int& nev, int& reach) {
+                                            const double* __restrict__ r2, double* phi, int wlo, int* ev_idx,
+                                            double* ev_div, int& nev, int& reach) {
     bool ok = true;
     int nev0 = nev;
-    int ief = nonrel ? hf_integ<WRITE, false, true>(e, c, v, xm1, xm2, xkr, r, r2, phi, ev_idx, ev_div, nev, reach, ok)
-                     : hf_integ<WRITE, false, false>(e, c, v, xm1, xm2, xkr, r, r2, phi, ev_idx, ev_div, nev, reach, ok);
+    int ief = nonrel ? hf_integ<WRITE, false, true>(e, c, v, xm1, xm2, xkr, r, r2, phi, wlo, ev_idx, ev_div, nev, reach, ok)
+                     : hf_integ<WRITE, false, false>(e, c, v, xm1, xm2, xkr, r, r2, phi, wlo, ev_idx, ev_div, nev, reach, ok);
     if (!ok) {
         nev = nev0;
-        ief = hf_integ<WRITE, true, false>(e, c, v, xm1, xm2, xkr, r, r2, phi, ev_idx, ev_div, nev, reach, ok);
+        ief = hf_integ<WRITE, true, false>(e, c, v, xm1, xm2, xkr, r, r2, phi, wlo, ev_idx, ev_div, nev, reach, ok);
     }
     return ief;
+}
+
+// ---- team sweeps ------------------------------------------------------------------------------------------------------
+// A cluster of eight CTAs leaves each CTA two or three orbitals and most of its warps idle, while the one warp of an orbital
+// is bound by the latency of ~80 dependent instructions per mesh point.  Only FIVE of them are the recurrence: everything
+// else -- t, xm, tm, the two coefficient quotients, xk, dk and the reciprocal of dk that the recurrence's own division needs
+// -- depends on the mesh point and the energy alone.  So the W warps of a team split the sweep in two: W-1 PRODUCER warps
+// tabulate A = 2 - dl5 xk, y ~ 1/dk and dk for 4 (W-1) mesh points x 32 energies per tile into shared memory, and the
+// CONSUMER warp runs nothing but the recurrence p2 = (A p1) / dk - p0 from those tables, one lane per energy, one tile
+// behind the producers (two buffers, one named barrier per tile).  Every value is produced by the same operations as in
+// hf_integ, so the verdicts and reaches are the same; an entry whose divisions left the validity window of the fast
+// division carries y = NaN, and a lane that meets one (or whose own quotients left the window) repeats its sweep with
+// hf_integ<EXACT>.
+template <bool NONREL, bool EXACT>
+__device__ __forceinline__ void hf_coef(double e, int i, const HfIntegConsts& c, const double* __restrict__ v,
+                                        const double* __restrict__ xm1, const double* __restrict__ xm2,
+                                        const double* __restrict__ xkr, const double* __restrict__ r2, double& xk, double& dk,
+                                        double& xm, DivTrack& trk) {
+    auto dv = [&](double x, double a) { return EXACT ? __ddiv_rn(x, a) : div_tracked(x, a, trk); };
+    const double t = __dsub_rn(e, v[i - 1]);
+    xm = __dadd_rn(1.0, __dmul_rn(c.a2, t));
+    const double tm = __dadd_rn(xm, xm);
+    double xmx, q4;
+    if (NONREL) {
+        xmx = xm1[i - 1];
+        q4 = __dmul_rn(xm2[i - 1], 0.5);
+    } else {
+        xmx = dv(xm1[i - 1], xm);
+        q4 = dv(xm2[i - 1], tm);
+    }
+    xk = __dsub_rn(
+        __dmul_rn(r2[i - 1], __dadd_rn(__dsub_rn(__dmul_rn(tm, t), __dmul_rn(xmx, __dadd_rn(xkr[i - 1], __dmul_rn(0.75, xmx)))),
+                                       q4)),
+        c.xl4);
+    dk = __dadd_rn(1.0, __dmul_rn(c.dl2, xk));
+}
+
+// p2/p1 > 1 of the blow-up test (:1108) without the division: for p1 != 0 the correctly rounded quotient exceeds 1 exactly
+// when the operands have one sign and |p2| > |p1| (the next double above |p1| is more than half an ulp of 1 away in ratio)
+__device__ __forceinline__ bool hf_ratio_gt1(double p2, double p1) {
+    if (p1 == 0.0) return __ddiv_rn(p2, p1) > 1.0;
+    return ((p2 > 0.0 && p1 > 0.0) || (p2 < 0.0 && p1 < 0.0)) && fabs(p2) > fabs(p1);
+}
+
+// One round of W warps over the energies e (lane = node of the bisection tree, the same in every warp of the team).
+// role < 0: consumer, else producer number role of NP.  `tiles`: this team's 2 x 4 NP x kHfEntry doubles;
+// `done`: this team's flag word in shared memory; rid: a number no earlier round of this team used.
+template <bool NONREL>
+__device__ __noinline__ void hf_team_round(double e, bool reachable, const HfIntegConsts& c, const double* __restrict__ v,
+                                           const double* __restrict__ xm1, const double* __restrict__ xm2,
+                                           const double* __restrict__ xkr, const double* __restrict__ r,
+                                           const double* __restrict__ r2, double* tiles, volatile int* done, int rid, int NP,
+                                           int role, int bar_id, bool force_exact, int& ief, int& reach) {
+    const int lane = threadIdx.x & 31, nr = c.nr, nnideal = c.nnideal;
+    int rch = 2;  // the sweep's reach (a local: the reference would live in memory)
+    const int T = 4 * NP, nthreads = 32 * (NP + 1);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    auto produce = [&](int k) {
+        double* tile = tiles + static_cast<size_t>(k & 1) * T * kHfEntry;
+        const int mbase = 2 + k * T;
+#pragma unroll 1
+        for (int s = role; s < T; s += NP) {
+            const int m = mbase + s;
+            if (m > nr - 1 || !reachable) continue;
+            DivTrack trk;
+            trk.reset();
+            double xk, dk, xm;
+            hf_coef<NONREL, false>(e, m, c, v, xm1, xm2, xkr, r2, xk, dk, xm, trk);
+            const double A = __dsub_rn(2.0, __dmul_rn(c.dl5, xk));
+            double y = div_fast_rcp(dk);
+            const float ah = fabsf(__int_as_float(__double2hiint(dk)));
+            if (!(trk.ok() && ah >= __int_as_float(0x3f700000) && ah <= __int_as_float(0x40f00000))) y = nan;
+            double* ent = tile + s * kHfEntry;
+            ent[lane] = A;
+            ent[32 + lane] = y;
+            ent[64 + lane] = dk;
+        }
+    };
+    // the consumer lane's sweep
+    double p0 = 0.0, p1 = 0.0;
+    int nn = 0, istop = 0, last = 0, verdict = 2;
+    bool active = false, bad = false;
+    float qmin = __int_as_float(0x7f000000), qmax = 0.0f;
+#ifdef PHSH_HF_PROFILE
+    long long pt0 = clock64();
+#endif
+    if (role < 0) {
+        if (reachable) {
+            DivTrack unused;
+            double xk0, dk0, xm0, xk2, dk2, xmm;
+            hf_coef<false, true>(e, 1, c, v, xm1, xm2, xkr, r2, xk0, dk0, xm0, unused);
+            hf_coef<false, true>(e, 2, c, v, xm1, xm2, xkr, r2, xk2, dk2, xmm, unused);
+            p0 = dk0;
+            p1 = __dmul_rn(__dmul_rn(dk2, __dsub_rn(c.pw12, __ddiv_rn(__dmul_rn(__dsub_rn(r[1], r[0]), c.z), c.xlp))),
+                           sqrt(__ddiv_rn(xm0, xmm)));
+            istop = hf_turning_point(e, c.vsm, nr);
+            if (istop == 0) {
+                verdict = -1;
+            } else {
+                active = true;
+                last = max(min(istop + 2, nr), nr - 1);
+            }
+        }
+    } else {
+        produce(0);
+    }
+    hf_team_bar(bar_id, nthreads);
+#ifdef PHSH_HF_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0) { hf_prof_g[0] += clock64() - pt0; pt0 = clock64(); }
+    long long pwait = 0, pt1 = 0;
+#endif
+    // one step with every test of integ in its place (the rare cases of a block of four, see below)
+    auto careful_step = [&](int i, double A, double y, double dk) {
+        const double q = div_fast_finish(__dmul_rn(A, p1), dk, y);
+        const float qh = fabsf(__int_as_float(__double2hiint(q)));
+        qmin = fminf(qmin, qh);
+        qmax = fmaxf(qmax, qh);
+        double p2 = __dsub_rn(q, p0);
+        if (y != y) {
+            bad = true;
+            active = false;
+        } else if (i > istop + 2 && __ddiv_rn(p2, p1) > 1.0) {
+            verdict = -1;
+            active = false;
+        } else {
+            rch = i;
+            if (fabs(p2) > 10000000000.0) {
+                p0 = __ddiv_rn(p0, p2);
+                p1 = __ddiv_rn(p1, p2);
+                p2 = __ddiv_rn(p2, p2);
+            }
+            if (__dmul_rn(p2, p1) < 0.0) {
+                nn = nn + 1;
+                if (nn > nnideal) {
+                    verdict = 1;
+                    active = false;
+                }
+            }
+            p0 = p1;
+            p1 = p2;
+            if (i >= last) active = false;
+        }
+    };
+    for (int k = 0;; ++k) {
+        if (role < 0) {
+            const double* tile = tiles + static_cast<size_t>(k & 1) * T * kHfEntry + lane;
+            const int ibase = 3 + k * T;  // the step that consumes entry s of this tile
+            // Four steps at a time.  The recurrence itself runs unconditionally, as one chain of 4 x 5 dependent operations
+            // (a lane that has finished computes on, unheeded); the tests of the four steps become flags, and the ends of a
+            // sweep (blow-up beyond the turning point, one node too many, the last mesh point) are read off the flags in the
+            // order of the steps.  Only what changes the values themselves -- the |p2| > 1e10 rescaling, a table entry
+            // outside the fast division's window -- sends the block through careful_step.
+            double A0 = tile[0], y0 = tile[32], d0 = tile[64];
+#pragma unroll 1
+            for (int s0 = 0; s0 < T; s0 += 4) {
+                const double* ent = tile + s0 * kHfEntry;
+                const double A1 = ent[kHfEntry], y1 = ent[kHfEntry + 32], d1 = ent[kHfEntry + 64];
+                const double A2 = ent[2 * kHfEntry], y2 = ent[2 * kHfEntry + 32], d2 = ent[2 * kHfEntry + 64];
+                const double A3 = ent[3 * kHfEntry], y3 = ent[3 * kHfEntry + 32], d3 = ent[3 * kHfEntry + 64];
+                const double big = 10000000000.0;
+                const double p0s = p0, p1s = p1;
+                const double qa = div_fast_finish(__dmul_rn(A0, p1s), d0, y0);
+                const double pa = __dsub_rn(qa, p0s);
+                const int na = __dmul_rn(pa, p1s) < 0.0 ? 1 : 0;
+                const double qb = div_fast_finish(__dmul_rn(A1, pa), d1, y1);
+                const double pb = __dsub_rn(qb, p1s);
+                const int nb = __dmul_rn(pb, pa) < 0.0 ? 1 : 0;
+                const double qc = div_fast_finish(__dmul_rn(A2, pb), d2, y2);
+                const double pc = __dsub_rn(qc, pa);
+                const int nc = __dmul_rn(pc, pb) < 0.0 ? 1 : 0;
+                const double qd = div_fast_finish(__dmul_rn(A3, pc), d3, y3);
+                const double pd = __dsub_rn(qd, pb);
+                const int nd = __dmul_rn(pd, pc) < 0.0 ? 1 : 0;
+                // (a NaN anywhere -- the y of an invalid entry included -- reaches pd, and fails its comparison)
+                const bool small = fabs(pa) <= big && fabs(pb) <= big && fabs(pc) <= big && fabs(pd) <= big;
+                p0 = pc;
+                p1 = pd;
+                const double Ac = A0, yc = y0, dc = d0;
+                if (s0 + 4 < T) {  // the first entry of the next block, ahead of the tests below
+                    A0 = ent[4 * kHfEntry];
+                    y0 = ent[4 * kHfEntry + 32];
+                    d0 = ent[4 * kHfEntry + 64];
+                }
+#ifdef PHSH_HF_PROFILE
+                if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[11] += 1;
+#endif
+                if (active) {
+                    const int i0 = ibase + s0;
+                    const float h0 = fabsf(__int_as_float(__double2hiint(qa))), h1 = fabsf(__int_as_float(__double2hiint(qb)));
+                    const float h2 = fabsf(__int_as_float(__double2hiint(qc))), h3 = fabsf(__int_as_float(__double2hiint(qd)));
+                    const bool tail = i0 + 3 > istop + 2;  // some step of the block takes the blow-up test
+                    bool plain = small, quiet = nn + na + nb + nc + nd <= nnideal && i0 + 3 < last;
+                    if (tail) {  // (all four quotients are tested, also where the block starts below istop + 3: conservative)
+                        plain = plain && p1s != 0.0 && pa != 0.0 && pb != 0.0 && pc != 0.0;
+                        auto gt1 = [](double p2, double pp) { return ((p2 > 0.0) == (pp > 0.0)) & (fabs(p2) > fabs(pp)); };
+                        quiet = quiet & !(gt1(pa, p1s) | gt1(pb, pa) | gt1(pc, pb) | gt1(pd, pc));
+                    }
+                    if (plain && quiet) {  // four more steps and nothing happened
+                        nn += na + nb + nc + nd;
+                        rch = i0 + 3;
+                        qmin = fminf(fminf(qmin, fminf(h0, h1)), fminf(h2, h3));
+                        qmax = fmaxf(fmaxf(qmax, fmaxf(h0, h1)), fmaxf(h2, h3));
+                    } else if (plain) {
+#ifdef PHSH_HF_PROFILE
+                        if (blockIdx.x == 0 && threadIdx.x < 32 && (threadIdx.x & 31) == __ffs(__activemask()) - 1) hf_prof_g[12] += 1;
+#endif
+                        bool go = true;
+                        auto resolve = [&](int i, double p2, double pp, float qh, int neg) {
+                            if (!go) return;
+                            qmin = fminf(qmin, qh);
+                            qmax = fmaxf(qmax, qh);
+                            if (i > istop + 2 && hf_ratio_gt1(p2, pp)) {
+                                verdict = -1;
+                                go = false;
+                                return;
+                            }
+                            rch = i;
+                            if (neg) {
+                                nn = nn + 1;
+                                if (nn > nnideal) {
+                                    verdict = 1;
+                                    go = false;
+                                    return;
+                                }
+                            }
+                            if (i >= last) go = false;
+                        };
+                        resolve(i0, pa, p1s, h0, na);
+                        resolve(i0 + 1, pb, pa, h1, nb);
+                        resolve(i0 + 2, pc, pb, h2, nc);
+                        resolve(i0 + 3, pd, pc, h3, nd);
+                        active = go;
+                    } else {
+#ifdef PHSH_HF_PROFILE
+                        if (blockIdx.x == 0 && threadIdx.x < 32 && (threadIdx.x & 31) == __ffs(__activemask()) - 1) hf_prof_g[13] += 1;
+#endif
+                        p0 = p0s;
+                        p1 = p1s;
+                        careful_step(i0, Ac, yc, dc);
+                        if (active) careful_step(i0 + 1, A1, y1, d1);
+                        if (active) careful_step(i0 + 2, A2, y2, d2);
+                        if (active) careful_step(i0 + 3, A3, y3, d3);
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, active) && lane == 0) *done = rid;
+        } else {
+            produce(k + 1);
+        }
+#ifdef PHSH_HF_PROFILE
+        pt1 = clock64();
+#endif
+        hf_team_bar(bar_id, nthreads);
+#ifdef PHSH_HF_PROFILE
+        pwait += clock64() - pt1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[8] += 1;
+#endif
+        if (*done == rid) break;
+    }
+#ifdef PHSH_HF_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0) { hf_prof_g[1] += clock64() - pt0; hf_prof_g[2] += pwait; }
+#endif
+    if (role < 0) {
+        ief = verdict != 2 ? verdict : (nn < nnideal ? -1 : 0);
+        reach = rch;
+        if (!(qmin >= __int_as_float(0x07f00000) && qmax <= __int_as_float(0x77f00000))) bad = true;
+        if (reachable && (bad || force_exact)) {
+            int nev = 0;
+            bool ok = true;
+            ief = hf_integ<false, true, false>(e, c, v, xm1, xm2, xkr, r, r2, nullptr, 0, nullptr, nullptr, nev, reach, ok);
+        }
+        if (!reachable) {
+            ief = 0;
+            reach = 0;
+        }
+    }
 }
 
 // grid = number of atoms x cluster size, block = kHfThreads threads (85 registers per thread for the two coefficient
@@ -280,6 +585,9 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
     __shared__ int nev_s[32];
     __shared__ double stk_e_s[32][kHfMaxStack];    // per warp: sweeps of the current bisection that still own entries of phi
     __shared__ int stk_reach_s[32][kHfMaxStack];
+    __shared__ double team_d_s[32][3];             // per team: el, eh, e_last after a round (written by its consumer warp)
+    __shared__ int team_i_s[32][4];                // status, stack height, 'replay all', the round that has finished
+    extern __shared__ __align__(16) double hf_dyn_s[];  // kHfDynSmem bytes: the coefficient tiles of the teams
 
     const double cl = 137.038;
     const double alpha = __ddiv_rn(P.rel, cl);
@@ -291,6 +599,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
     const double ratio = P.ratio, ratio1 = __dsub_rn(1.0, P.ratio);
 
     const bool nonrel = a2 == 0.0;  // then xm == 1 and tm == 2 exactly in integ
+    for (int i = tid_l; i < 32; i += nth_l) team_i_s[i][3] = 0;
     for (int i = tid; i < nel; i += nth) P.ev[i] = 0.0;
     // xkappa / r(j) of integ :1077, the same for every energy and every iteration (xkappa as in elsolve :750-752)
     for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
@@ -316,6 +625,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
     };
     unsigned long long t_elsolve = 0, t_getpot = 0, t_mark = 0;
     int iter = 0;
+    int team_round = 0;  // rounds this warp's team has run (the same number in every warp of the team)
     for (;;) {
         // ---- setqmm (:844-931), njrc = 0: v, xm1, xm2 of every orbital ------------------------------------------
         for (long k = tid; k < static_cast<long>(nel) * nr; k += nth) {
@@ -340,12 +650,40 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
             xm2[nr - 1] = xm2[nr - 2];
             xm1[0] = __dsub_rn(__dadd_rn(xm1[1], __ddiv_rn(za2, r2[1])), __ddiv_rn(za2, r2[0]));
             xm2[0] = __dadd_rn(__dsub_rn(xm2[1], __ddiv_rn(__ddiv_rn(zaa, r2[1]), r[1])), __ddiv_rn(__ddiv_rn(zaa, r2[0]), r[0]));
+            // suffix minima of v for hf_turning_point (an entry that compares false, a NaN, is skipped as the scan skips it)
+            const double* vo = P.v + static_cast<long>(o) * nr;
+            double* sm = P.vsm + static_cast<long>(o) * nr;
+            double mn = __longlong_as_double(0x7ff0000000000000LL);
+            sm[nr - 1] = mn;
+            for (int j = nr - 1; j >= 1; --j) {
+                const double vj = vo[j - 1];
+                mn = vj < mn ? vj : mn;
+                sm[j - 1] = mn;
+            }
         }
         hf_cluster_sync();
 
         // ---- elsolve (:742-793): one warp per orbital, five bisection levels per round ---------------------------
+        // (a team of W warps per orbital where the CTA has at least four times as many warps as orbitals: hf_team_round)
         if (tid == 0) t_mark = now_ns();
-        for (int o = crank + csize * warp; o < nel; o += csize * nwarps_l) {
+        int W = 1;
+        {
+            const int per_cta = (nel + csize - 1) / csize;
+            while (W < kHfTeamMaxW && 2 * W * per_cta <= nwarps_l) W *= 2;
+            if (W < 4 || P.team_mode == 1 || nwarps_l % W != 0) W = 1;
+        }
+        // The consumer of a team is its first warp: a multiple of four, so that the consumers share one of the SM's four
+        // schedulers with each other only -- next to producer warps, which always have an instruction ready, each dependent
+        // instruction of the recurrence waited four times as long for its issue slot.  (A team of eight leaves its fifth
+        // warp, the other one of that scheduler, idle.)
+        const int team = warp / W, nteams = nwarps_l / W, wt = warp % W;
+        const bool consumer = wt == 0;  // ... which also walks the tree and finishes the orbital
+        const bool idle = W == 8 && wt == 4;
+        const int NP = W == 8 ? 6 : W - 1;
+        const int role = consumer ? -1 : wt - 1 - (W == 8 && wt > 4 ? 1 : 0);
+        const int cwarp = team * W, members = NP + 1, member = role + 1;
+        double* tiles = hf_dyn_s + static_cast<size_t>(team) * 2 * 4 * NP * kHfEntry;
+        for (int o = idle ? nel : crank + csize * team; o < nel; o += csize * nteams) {
             const double* v = P.v + static_cast<long>(o) * nr;
             const double* xm1 = P.xm1 + static_cast<long>(o) * nr;
             const double* xm2 = P.xm2 + static_cast<long>(o) * nr;
@@ -369,6 +707,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
             c.xkappa = xkappa;
             c.nnideal = n - l - 1;
             c.nr = nr;
+            c.vsm = P.vsm + static_cast<long>(o) * nr;
             double el = __ddiv_rn(__dmul_rn(-P.z, P.z), static_cast<double>(n * n));
             double eh = 0.0;
             const double etol = 0.0000000001;
@@ -382,6 +721,9 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
             bool replay_all = false;  // stack overflow (never seen): fall back to replaying nothing but the last sweep
             // node of this lane in the 5-level tree: depth d, index idx within the level
             const int d_me = 31 - __clz(lane + 1), idx_me = lane + 1 - (1 << d_me);
+#ifdef PHSH_HF_PROFILE
+            long long pk0 = clock64();
+#endif
             while (status == 0) {
                 // the interval this lane's node would see if the bisection took the path that leads to it
                 double el_n = el, eh_n = eh;
@@ -399,13 +741,22 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                 const double e_n = __ddiv_rn(__dadd_rn(el_n, eh_n), 2.0);
                 int nev_dummy = 0, reach_n = 0;
                 int ief_n = 0;
-                if (reachable)
-                    ief_n = hf_integ_any<false>(nonrel, e_n, c, v, xm1, xm2, xkr, r, r2, nullptr, nullptr, nullptr, nev_dummy,
+                if (W > 1) {
+                    ++team_round;
+                    if (nonrel)
+                        hf_team_round<true>(e_n, reachable, c, v, xm1, xm2, xkr, r, r2, tiles, &team_i_s[team][3], team_round, NP,
+                                            role, 1 + team, P.team_mode == 2, ief_n, reach_n);
+                    else
+                        hf_team_round<false>(e_n, reachable, c, v, xm1, xm2, xkr, r, r2, tiles, &team_i_s[team][3], team_round, NP,
+                                             role, 1 + team, P.team_mode == 2, ief_n, reach_n);
+                } else if (reachable) {
+                    ief_n = hf_integ_any<false>(nonrel, e_n, c, v, xm1, xm2, xkr, r, r2, nullptr, 0, nullptr, nullptr, nev_dummy,
                                                 reach_n);
+                }
                 __syncwarp();
-                // walk the tree with the actual verdicts (every lane does the same walk)
+                // walk the tree with the actual verdicts (every lane of the consumer warp does the same walk)
                 int d = 0, idx = 0;
-                while (d < 5) {
+                while (consumer && d < 5) {
                     const int src = (1 << d) - 1 + idx;
                     const int ief = __shfl_sync(0xffffffffu, ief_n, src);
                     const int rch = __shfl_sync(0xffffffffu, reach_n, src);
@@ -437,25 +788,53 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                     idx = 2 * idx + (ief == 1 ? 1 : 0);
                     ++d;
                 }
+                if (W > 1) {  // the consumer's verdict reaches the producers
+                    if (consumer && lane == 0) {
+                        team_d_s[team][0] = el;
+                        team_d_s[team][1] = eh;
+                        team_d_s[team][2] = e_last;
+                        team_i_s[team][0] = status;
+                        team_i_s[team][1] = nstk;
+                        team_i_s[team][2] = replay_all ? 1 : 0;
+                    }
+                    hf_team_bar(1 + team, 32 * members);
+                    el = team_d_s[team][0];
+                    eh = team_d_s[team][1];
+                    e_last = team_d_s[team][2];
+                    status = team_i_s[team][0];
+                    nstk = team_i_s[team][1];
+                    replay_all = team_i_s[team][2] != 0;
+                    hf_team_bar(1 + team, 32 * members);
+                }
             }
-            // replay the owning sweeps, oldest first; the last one is the sweep at the final energy
+#ifdef PHSH_HF_PROFILE
+            if (blockIdx.x == 0 && threadIdx.x == 0) { hf_prof_g[3] += clock64() - pk0; hf_prof_g[9] += nstk; hf_prof_g[10] += 1; }
+            pk0 = clock64();
+#endif
+            // replay the owning sweeps (the last one is the sweep at the final energy): sweep q owns the entries
+            // above the reach of sweep q + 1, so the sweeps write disjoint ranges and the warps of a team share them out
             if (replay_all) {
                 nstk = 1;
-                if (lane == 0) stk_e_s[warp][0] = e_last;
+                if (consumer && lane == 0) {
+                    stk_e_s[warp][0] = e_last;
+                    stk_reach_s[warp][0] = nr;
+                }
+                if (W > 1) hf_team_bar(1 + team, 32 * members);
                 __syncwarp();
             }
-            for (int q = 0; q < nstk; ++q) {
+            for (int q = member; q < nstk; q += members) {
+                const int wlo = q + 1 < nstk ? stk_reach_s[cwarp][q + 1] : 0;
                 if (lane == 0) {
                     int nev = 0, rch = 0;
-                    hf_integ_any<true>(nonrel, stk_e_s[warp][q], c, v, xm1, xm2, xkr, r, r2, phi, ev_idx_s[warp], ev_div_s[warp],
-                                       nev, rch);
+                    hf_integ_any<true>(nonrel, stk_e_s[cwarp][q], c, v, xm1, xm2, xkr, r, r2, phi, wlo, ev_idx_s[warp],
+                                       ev_div_s[warp], nev, rch);
                     nev_s[warp] = nev;
                 }
                 __syncwarp();
                 // the rescalings of that sweep: entry j was divided by every later event's p2, in order
                 const int nev = nev_s[warp];
                 if (nev > 0)
-                    for (int j = 1 + lane; j <= nr; j += 32) {
+                    for (int j = wlo + 1 + lane; j <= nr; j += 32) {
                         double x = phi[j - 1];
                         for (int k = 0; k < nev; ++k)
                             if (ev_idx_s[warp][k] >= j) x = __ddiv_rn(x, ev_div_s[warp][k]);
@@ -463,6 +842,15 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                     }
                 __syncwarp();
             }
+            if (W > 1) {
+                __threadfence_block();  // phi is global memory: the consumer reads what its team mates wrote
+                hf_team_bar(1 + team, 32 * members);
+                if (!consumer) continue;
+            }
+#ifdef PHSH_HF_PROFILE
+            if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[4] += clock64() - pk0;
+            pk0 = clock64();
+#endif
             if (lane == 0) {
                 P.evnew[o] = e_last;
                 P.statusd[o] = static_cast<double>(status);
@@ -502,9 +890,12 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                     for (int j = lane; j < nr; j += 32) phi[j] = phi2[j];
                     __syncwarp();
                 }
+                // the terms by all lanes, their sum in the Fortran's order by one
+                for (int j = lane; j < nr; j += 32) phi2[j] = __dmul_rn(__dmul_rn(phi[j], phi[j]), dr[j]);
+                __syncwarp();
                 if (lane == 0) {
                     double s = 0.0;
-                    for (int j = 0; j < nr; ++j) s = __dadd_rn(s, __dmul_rn(__dmul_rn(phi[j], phi[j]), dr[j]));
+                    for (int j = 0; j < nr; ++j) s = __dadd_rn(s, phi2[j]);
                     xnorm_s[o] = sqrt(s);
                 }
                 __syncwarp();
@@ -513,22 +904,33 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                 __syncwarp();
             }
             // kinetic energy (:416-427)
-            if (lane == 0) {
+            {
                 const double evi = e_last;
                 const double* orb = P.orb + static_cast<long>(o) * nr;
-                double ekk = 0.0;
-                int ll = 2;
-                for (int j = nr; j >= 1; --j) {
+                for (int j = nr - lane; j >= 1; j -= 32) {  // ll = 2, 4, 2, ... from j = nr downwards
                     const double dq = __dmul_rn(phi[j - 1], phi[j - 1]);
-                    ekk = __dadd_rn(ekk, __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dsub_rn(evi, orb[j - 1]), dr[j - 1]), dq),
-                                                             static_cast<double>(ll)),
-                                                   3.0));
-                    ll = 6 - ll;
+                    const double ll = ((nr - j) & 1) ? 4.0 : 2.0;
+                    phi2[j - 1] = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dsub_rn(evi, orb[j - 1]), dr[j - 1]), dq), ll), 3.0);
                 }
-                P.ek[o] = ekk;
+                __syncwarp();
+                if (lane == 0) {
+                    double ekk = 0.0;
+                    for (int j = nr; j >= 1; --j) ekk = __dadd_rn(ekk, phi2[j - 1]);
+                    P.ek[o] = ekk;
+                }
+                __syncwarp();
             }
+#ifdef PHSH_HF_PROFILE
+            if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[5] += clock64() - pk0;
+#endif
         }
+#ifdef PHSH_HF_PROFILE
+        const long long pk1 = clock64();
+#endif
         hf_cluster_sync();
+#ifdef PHSH_HF_PROFILE
+        if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[6] += clock64() - pk1;
+#endif
         if (tid == 0) {
             const unsigned long long t = now_ns();
             t_elsolve += t - t_mark;
@@ -821,6 +1223,14 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         P.info[1] = static_cast<double>(iter);
         P.info[2] = static_cast<double>(mixing);
         P.info[3] = __ddiv_rn(__dmul_rn(P.scal[1], ratio1), ratio);
+#ifdef PHSH_HF_PROFILE
+        printf("hf profile (Mcycles, CTA 0 warp 0): round prologue %.2f, tiles %.2f (of which barrier wait %.2f), %llu tiles | bisection %.2f, "
+               "replay %.2f (%llu sweeps / %llu orbital solves), tail %.2f, wait for the other CTAs %.2f\n",
+               hf_prof_g[0] * 1e-6, hf_prof_g[1] * 1e-6, hf_prof_g[2] * 1e-6, hf_prof_g[8], hf_prof_g[3] * 1e-6, hf_prof_g[4] * 1e-6,
+               hf_prof_g[9], hf_prof_g[10], hf_prof_g[5] * 1e-6, hf_prof_g[6] * 1e-6);
+        printf("   blocks of four %llu, with an ordered resolve %llu, with careful steps %llu\n", hf_prof_g[11], hf_prof_g[12], hf_prof_g[13]);
+        for (int k = 0; k < 16; ++k) hf_prof_g[k] = 0;
+#endif
         P.info[6] = static_cast<double>(t_elsolve);
         P.info[7] = static_cast<double>(t_getpot);
     }

@@ -105,6 +105,24 @@ def test_results_do_not_depend_on_the_cluster_size(hio, monkeypatch):
             assert np.array_equal(g["rho"], w["rho"]) and np.array_equal(g["ev"][: len(w["ev"])], w["ev"]), c
 
 
+def test_results_do_not_depend_on_how_the_sweeps_are_run(hio, monkeypatch):
+    """Where a CTA has warps to spare an orbital gets a team of 4 or 8 warps (coefficient tables by producer warps, the bare
+    recurrence by one consumer warp, the owning sweeps replayed in parallel).  PHSH_B200_HARTFOCK_TEAM = 1 keeps one warp per
+    orbital, = 2 sends every team sweep through its exact repeat (the path an out-of-window division takes): the same bits
+    in all three modes, for a relativistic and a non-relativistic atom, alone (teams of 8) and in one batch."""
+    from phaseshifts_b200 import api
+    atoms = [dict(z=6, nr=1000, rel=1.0, orbitals=C_ORB), dict(z=3, nr=800, rel=0.0, orbitals=[(1, 0, 0, -0.5, 1, 2.0), (2, 0, 0, -0.5, 1, 1.0)])]
+    want = [_oracle(hio, a["z"], a["nr"], a["rel"], 0.0, 0, a["orbitals"]) for a in atoms]
+    for mode in (0, 1, 2):
+        monkeypatch.setenv("PHSH_B200_HARTFOCK_TEAM", str(mode))
+        for c in (1, 8):
+            monkeypatch.setenv("PHSH_B200_HARTFOCK_CLUSTER", str(c))
+            got = api.hartfock_batch(atoms)
+            for g, w in zip(got, want):
+                assert g["scf_iterations"] == w["scf_iterations"], (mode, c)
+                assert np.array_equal(g["rho"], w["rho"]) and np.array_equal(g["ev"][: len(w["ev"])], w["ev"]), (mode, c)
+
+
 def test_shell_averaging_and_local_exchange_modes(hio):
     from phaseshifts_b200 import api
     for iuflag in (1, 2):
