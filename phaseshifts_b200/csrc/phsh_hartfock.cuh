@@ -564,6 +564,151 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
     }
 }
 
+// ---- getpot, one WARP per term ---------------------------------------------------------------------------------------
+// With a cluster on one atom there are more warps than terms per warp-width, and a thread that scans r alone is bound by
+// the latency of ~130 dependent-ish instructions per mesh point.  Of those only the running sums are serial: the warp
+// computes the addends of a chunk of mesh points in parallel into shared memory (w = q1 or -q2), a few lanes run the bare
+// recurrences x = (x + w(k)) + w(k-1) over the chunk (one lane per running sum, the same code for all: xout - q2 - q2p is
+// xout + (-q2) + (-q2p) bit for bit), and the warp turns the sums into the contributions in parallel again.  Operations
+// and their order are those of the one-thread scan (scan_term in the kernel), so the contributions are the same bits.
+constexpr int kHfChunk = 128;  // mesh points per chunk: 4 arrays x 128 doubles of shared memory per warp
+
+template <bool FAST>
+__device__ __noinline__ bool hf_term_warp(const HfProblem& P, const HfTerm& T, int t, double* sm, double& etot_part) {
+    const int lane = threadIdx.x & 31, nr = P.nr;
+    const bool direct = T.kind == 0;
+    const double* __restrict__ dr = P.dr;
+    const double* pi = P.phe + static_cast<long>(T.i) * nr;
+    const double* pj = P.phe + static_cast<long>(T.j) * nr;
+    const double* __restrict__ rpa = P.rpower + static_cast<long>(T.la) * nr;
+    const double* __restrict__ rpb = P.rpower + static_cast<long>(T.la + 1) * nr;
+    const double* __restrict__ rpi = P.rpinv + static_cast<long>(T.la + 1) * nr;
+    double* ci = P.contrib + (static_cast<long>(t) * 2 + 0) * nr;  // added to orb(:, i)
+    double* cj = P.contrib + (static_cast<long>(t) * 2 + 1) * nr;  // added to orb(:, j)
+    double* w0 = sm;                 // xout of channel i (the only channel of an exchange term)
+    double* w1 = sm + kHfChunk;      // xout of channel j
+    double* w2 = sm + 2 * kHfChunk;  // xint of channel i
+    double* w3 = sm + 3 * kHfChunk;  // xint of channel j
+    unsigned nlo = 0x7ff00000u, nhi = 0u;
+    auto half = [&](double x) { return FAST ? __dmul_rn(x, 0.5) : __ddiv_rn(x, 2.0); };
+    auto quo = [&](double x, double b, double y) {
+        if (!FAST) return __ddiv_rn(x, b);
+        const unsigned h = static_cast<unsigned>(__double2hiint(x)) & 0x7fffffffu;
+        nlo = min(nlo, x == 0.0 ? 0x7ff00000u : h);
+        nhi = max(nhi, h);
+        return cp_div(x, b, y);
+    };
+    auto q0i = [&](int k) { return half(__dmul_rn(__dmul_rn(dr[k], pi[k]), direct ? pi[k] : pj[k])); };
+    auto q0j = [&](int k) { return half(__dmul_rn(__dmul_rn(dr[k], pj[k]), pj[k])); };
+    const bool serial = lane < 4 && (direct || !(lane & 1));  // lanes 0, 1: xout of i, j; lanes 2, 3: xint of i, j
+    double* wl = sm + (lane & 3) * kHfChunk;
+    // the sums over all r that xout starts from
+    double S = 0.0;
+    for (int c0 = 0; c0 < nr; c0 += kHfChunk) {
+        const int n = min(kHfChunk, nr - c0);
+        for (int u = lane; u < n; u += 32) {
+            const int k = c0 + u;
+            const double b = rpb[k], y = rpi[k];
+            w0[u] = b != 0.0 ? quo(q0i(k), b, y) : 0.0;
+            if (direct) w1[u] = b != 0.0 ? quo(q0j(k), b, y) : 0.0;
+        }
+        __syncwarp();
+        if (serial && lane < 2)
+            for (int u = 0; u < n; ++u) S = __dadd_rn(S, wl[u]);
+        __syncwarp();
+    }
+    // mesh point 1
+    double x = 0.0, prev = 0.0;
+    if (serial) {
+        const double q0 = (lane & 1) ? q0j(0) : q0i(0);
+        if (lane < 2) {
+            const double q2p = rpb[0] != 0.0 ? quo(q0, rpb[0], rpi[0]) : 0.0;
+            x = __dsub_rn(__dmul_rn(2.0, S), q2p);
+            prev = -q2p;
+        } else {
+            prev = __dmul_rn(q0, rpa[0]);
+            x = prev;
+        }
+    }
+    if (lane == 0) {
+        ci[0] = 0.0;
+        cj[0] = 0.0;
+    }
+    const double xnum2 = __dmul_rn(P.xnum, P.xnum);
+    double epart = 0.0;
+    for (int c0 = 1; c0 < nr; c0 += kHfChunk) {
+        const int n = min(kHfChunk, nr - c0);
+        for (int u = lane; u < n; u += 32) {
+            const int k = c0 + u;
+            const double a = rpa[k], b = rpb[k], y = rpi[k];
+            const double qi0 = q0i(k);
+            w0[u] = -(b != 0.0 ? quo(qi0, b, y) : 0.0);
+            w2[u] = __dmul_rn(qi0, a);
+            if (direct) {
+                const double qj0 = q0j(k);
+                w1[u] = -(b != 0.0 ? quo(qj0, b, y) : 0.0);
+                w3[u] = __dmul_rn(qj0, a);
+            }
+        }
+        __syncwarp();
+        if (serial)
+            for (int u = 0; u < n; ++u) {
+                const double wk = wl[u];
+                x = __dadd_rn(__dadd_rn(x, wk), prev);
+                prev = wk;
+                wl[u] = x;
+            }
+        __syncwarp();
+        for (int u = lane; u < n; u += 32) {
+            const int k = c0 + u;
+            const double a = rpa[k], b = rpb[k], y = rpi[k];
+            const double qi0 = q0i(k);
+            if (direct) {
+                const double qj0 = q0j(k);
+                double vali = __dmul_rn(w0[u], a);
+                if (b != 0.0) vali = __dadd_rn(vali, quo(w2[u], b, y));
+                cj[k] = __dmul_rn(T.ri, vali);
+                double valj = __dmul_rn(w1[u], a);
+                if (b != 0.0) valj = __dadd_rn(valj, quo(w3[u], b, y));
+                ci[k] = __dmul_rn(T.rj, valj);
+                w0[u] = __dmul_rn(T.rc, __dadd_rn(__dmul_rn(qi0, valj), __dmul_rn(qj0, vali)));
+            } else {
+                double to_i = 0.0, to_j = 0.0, e = 0.0;
+                if (qi0 != 0.0) {
+                    double val = __dmul_rn(w0[u], a);
+                    if (b != 0.0) val = __dadd_rn(val, quo(w2[u], b, y));
+                    e = -__dmul_rn(__dmul_rn(__dmul_rn(2.0, qi0), T.rc), val);
+                    double xx = __ddiv_rn(pj[k], pi[k]);
+                    if (__ddiv_rn(fabs(xx), P.xnum) > 1.0)
+                        to_i = -__dmul_rn(__ddiv_rn(__dmul_rn(T.rj, xnum2), xx), val);
+                    else
+                        to_i = -__dmul_rn(__dmul_rn(T.rj, xx), val);
+                    xx = __ddiv_rn(pi[k], pj[k]);
+                    if (__ddiv_rn(fabs(xx), P.xnum) > 1.0)
+                        to_j = -__dmul_rn(__ddiv_rn(__dmul_rn(T.ri, xnum2), xx), val);
+                    else
+                        to_j = -__dmul_rn(__dmul_rn(T.ri, xx), val);
+                }
+                ci[k] = to_i;
+                cj[k] = to_j;
+                w0[u] = e;
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            for (int u = 0; u < n; ++u) epart = __dadd_rn(epart, w0[u]);  // (a skipped point adds 0: epart is never -0)
+        __syncwarp();
+    }
+    bool ok = true;
+    if (FAST) {
+        nlo = __reduce_min_sync(0xffffffffu, nlo);
+        nhi = __reduce_max_sync(0xffffffffu, nhi);
+        ok = nlo >= 0x07b00000u && nhi <= 0x71f00000u;
+    }
+    if (ok && lane == 0) etot_part = __dadd_rn(etot_part, epart);
+    return ok;
+}
+
 // grid = number of atoms x cluster size, block = kHfThreads threads (85 registers per thread for the two coefficient
 // chains of hf_integ).  The CTAs of a cluster share one atom: orbitals (elsolve) and pair terms (getpot) are dealt round
 // robin over the CTAs, element-wise loops are split in blocks; everything order-dependent keeps its order, so the
@@ -1063,9 +1208,19 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
             if (ok) etot_part = __dadd_rn(etot_part, epart);
             return ok;
         };
-        for (int t = tid_l * csize + crank; t < P.nterms; t += nth) {
-            const HfTerm T = P.terms[t];
-            if (!(P.rpinv_ok && scan_term(T, t, std::true_type()))) scan_term(T, t, std::false_type());
+        if (P.team_mode != 1 && P.nterms <= 8 * nwarps) {
+            // more warps than terms per warp-width: one warp per term (hf_term_warp), dealt like the threads below
+            double* sm = hf_dyn_s + static_cast<size_t>(warp) * 4 * kHfChunk;
+            for (int t = warp * csize + crank; t < P.nterms; t += nwarps) {
+                const HfTerm T = P.terms[t];
+                if (!(P.rpinv_ok && P.team_mode != 2 && hf_term_warp<true>(P, T, t, sm, etot_part)))
+                    hf_term_warp<false>(P, T, t, sm, etot_part);
+            }
+        } else {
+            for (int t = tid_l * csize + crank; t < P.nterms; t += nth) {
+                const HfTerm T = P.terms[t];
+                if (!(P.rpinv_ok && scan_term(T, t, std::true_type()))) scan_term(T, t, std::false_type());
+            }
         }
         hf_cluster_sync();
         if (tid == 0) t_getpot += now_ns() - t_mark;
