@@ -442,6 +442,10 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
 #pragma unroll 1
             for (int s0 = 0; s0 < T; s0 += 4) {
                 const double* ent = tile + s0 * kHfEntry;
+#ifdef PHSH_HF_PROFILE
+                long long pb0, pb1;
+                asm volatile("mov.u64 %0, %%clock64;" : "=l"(pb0) : "d"(p1));
+#endif
                 const double A1 = ent[kHfEntry], y1 = ent[kHfEntry + 32], d1 = ent[kHfEntry + 64];
                 const double A2 = ent[2 * kHfEntry], y2 = ent[2 * kHfEntry + 32], d2 = ent[2 * kHfEntry + 64];
                 const double A3 = ent[3 * kHfEntry], y3 = ent[3 * kHfEntry + 32], d3 = ent[3 * kHfEntry + 64];
@@ -458,6 +462,10 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
                 const int nc = __dmul_rn(pc, pb) < 0.0 ? 1 : 0;
                 const double qd = div_fast_finish(__dmul_rn(A3, pc), d3, y3);
                 const double pd = __dsub_rn(qd, pb);
+#ifdef PHSH_HF_PROFILE
+                asm volatile("mov.u64 %0, %%clock64;" : "=l"(pb1) : "d"(pd));
+                if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[14] += pb1 - pb0;
+#endif
                 const int nd = __dmul_rn(pd, pc) < 0.0 ? 1 : 0;
                 // (a NaN anywhere -- the y of an invalid entry included -- reaches pd, and fails its comparison)
                 const bool small = fabs(pa) <= big && fabs(pb) <= big && fabs(pc) <= big && fabs(pd) <= big;
@@ -564,6 +572,112 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
     }
 }
 
+// ---- the replayed sweep, by a whole warp ---------------------------------------------------------------------------------
+// hf_integ<WRITE> on one lane costs ~800 cycles per mesh point, nearly all of it the coefficients, the square root and the
+// quotient of phi -- none of which depend on the recurrence.  Here the 32 lanes tabulate A, y, dk and sqrt(xm r) of 32
+// consecutive mesh points into shared memory (all quotients by IEEE division: in parallel they cost little), lane 0 runs
+// the 31 recurrence steps they allow with every test of integ in its place, and the lanes then store phi = p2 sq / dk of
+// those steps together.  `wk`: 5 x 32 doubles of shared memory of this warp.  Returns false if the event list overflowed
+// (never for a physical atom): the caller repeats the sweep with hf_integ_any<true>.
+__device__ __noinline__ bool hf_sweep_write_warp(double e, const HfIntegConsts& c, const double* __restrict__ v,
+                                                 const double* __restrict__ xm1, const double* __restrict__ xm2,
+                                                 const double* __restrict__ xkr, const double* __restrict__ r,
+                                                 const double* __restrict__ r2, double* phi, int wlo, int* ev_idx,
+                                                 double* ev_div, int& nev_out, double* wk) {
+    const int lane = threadIdx.x & 31, nr = c.nr, nnideal = c.nnideal;
+    const double dl5 = c.dl5;
+    double* sA = wk;
+    double* sy = wk + 32;
+    double* sd = wk + 64;
+    double* sq = wk + 96;
+    double* sp = wk + 128;  // p2 of the steps, as computed (before any rescaling)
+    DivTrack unused;
+    double p0 = 0.0, p1 = 0.0;
+    int nn = 0, nev = 0;
+    bool overflow = false;
+    // the start (:1045-1057) -- every lane computes it, lane 0 stores
+    double xk0, dk0, xm0, xk2, dk2, xmm;
+    hf_coef<false, true>(e, 1, c, v, xm1, xm2, xkr, r2, xk0, dk0, xm0, unused);
+    hf_coef<false, true>(e, 2, c, v, xm1, xm2, xkr, r2, xk2, dk2, xmm, unused);
+    p0 = dk0;
+    p1 = __dmul_rn(__dmul_rn(dk2, __dsub_rn(c.pw12, __ddiv_rn(__dmul_rn(__dsub_rn(r[1], r[0]), c.z), c.xlp))),
+                   sqrt(__ddiv_rn(xm0, xmm)));
+    if (lane == 0) {
+        if (wlo < 1) phi[0] = __ddiv_rn(__dmul_rn(p0, sqrt(__dmul_rn(xm0, r[0]))), dk0);
+        if (wlo < 2) phi[1] = __ddiv_rn(__dmul_rn(p1, sqrt(__dmul_rn(xmm, r[1]))), dk2);
+    }
+    const int istop = hf_turning_point(e, c.vsm, nr);
+    nev_out = 0;
+    if (istop == 0) return true;
+    const int last = max(min(istop + 2, nr), nr - 1);
+    for (int i0 = 3; i0 <= last; i0 += 31) {
+        // lane L: mesh point i0 - 1 + L, whose A, y, dk step i0 + L consumes and whose sq, dk step i0 + L - 1 stores with
+        {
+            const int m = min(i0 - 1 + lane, nr);
+            double xk, dk, xm;
+            hf_coef<false, true>(e, m, c, v, xm1, xm2, xkr, r2, xk, dk, xm, unused);
+            const float ah = fabsf(__int_as_float(__double2hiint(dk)));
+            const bool fast = ah >= __int_as_float(0x3f700000) && ah <= __int_as_float(0x40f00000);
+            sA[lane] = __dsub_rn(2.0, __dmul_rn(dl5, xk));
+            sy[lane] = fast ? div_fast_rcp(dk) : __longlong_as_double(0x7ff8000000000000LL);
+            sd[lane] = dk;
+            sq[lane] = sqrt(__dmul_rn(xm, r[m - 1]));
+        }
+        __syncwarp();
+        int done = 0, nsteps = 0;  // done: the sweep ended inside this chunk; nsteps: steps of the chunk that store phi
+        if (lane == 0) {
+            for (int L = 0; L < 31; ++L) {
+                const int i = i0 + L;
+                if (i > last) {
+                    done = 1;
+                    break;
+                }
+                const double y = sy[L], dk = sd[L], num = __dmul_rn(sA[L], p1);
+                double q = div_fast_finish(num, dk, y);
+                const float qh = fabsf(__int_as_float(__double2hiint(q)));
+                if (!(y == y && qh >= __int_as_float(0x07f00000) && qh <= __int_as_float(0x77f00000))) q = __ddiv_rn(num, dk);
+                double p2 = __dsub_rn(q, p0);
+                if (i > istop + 2 && __ddiv_rn(p2, p1) > 1.0) {
+                    done = 1;
+                    break;
+                }
+                sp[L] = p2;
+                nsteps = L + 1;
+                if (fabs(p2) > 10000000000.0) {
+                    if (nev < kHfMaxEvents) {
+                        ev_idx[nev] = i;
+                        ev_div[nev] = p2;
+                        ++nev;
+                    } else {
+                        overflow = true;
+                    }
+                    p0 = __ddiv_rn(p0, p2);
+                    p1 = __ddiv_rn(p1, p2);
+                    p2 = __ddiv_rn(p2, p2);
+                }
+                if (__dmul_rn(p2, p1) < 0.0) {
+                    nn = nn + 1;
+                    if (nn > nnideal) {
+                        done = 1;
+                        break;
+                    }
+                }
+                p0 = p1;
+                p1 = p2;
+            }
+        }
+        __syncwarp();
+        done = __shfl_sync(0xffffffffu, done, 0);
+        nsteps = __shfl_sync(0xffffffffu, nsteps, 0);
+        if (lane < nsteps && i0 + lane > wlo) phi[i0 + lane - 1] = __ddiv_rn(__dmul_rn(sp[lane], sq[lane + 1]), sd[lane + 1]);
+        __syncwarp();
+        if (done) break;
+    }
+    overflow = __shfl_sync(0xffffffffu, overflow ? 1 : 0, 0) != 0;
+    nev_out = __shfl_sync(0xffffffffu, nev, 0);
+    return !overflow;
+}
+
 // ---- getpot, one WARP per term ---------------------------------------------------------------------------------------
 // With a cluster on one atom there are more warps than terms per warp-width, and a thread that scans r alone is bound by
 // the latency of ~130 dependent-ish instructions per mesh point.  Of those only the running sums are serial: the warp
@@ -613,8 +727,17 @@ __device__ __noinline__ bool hf_term_warp(const HfProblem& P, const HfTerm& T, i
             if (direct) w1[u] = b != 0.0 ? quo(q0j(k), b, y) : 0.0;
         }
         __syncwarp();
-        if (serial && lane < 2)
-            for (int u = 0; u < n; ++u) S = __dadd_rn(S, wl[u]);
+        if (serial && lane < 2) {
+            int u = 0;
+            for (; u + 8 <= n; u += 8) {  // (the loads of eight steps ahead of their chain of additions)
+                double a8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a8[j] = wl[u + j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) S = __dadd_rn(S, a8[j]);
+            }
+            for (; u < n; ++u) S = __dadd_rn(S, wl[u]);
+        }
         __syncwarp();
     }
     // mesh point 1
@@ -651,13 +774,28 @@ __device__ __noinline__ bool hf_term_warp(const HfProblem& P, const HfTerm& T, i
             }
         }
         __syncwarp();
-        if (serial)
-            for (int u = 0; u < n; ++u) {
+        if (serial) {
+            int u = 0;
+            for (; u + 8 <= n; u += 8) {
+                double a8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a8[j] = wl[u + j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    x = __dadd_rn(__dadd_rn(x, a8[j]), prev);
+                    prev = a8[j];
+                    a8[j] = x;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wl[u + j] = a8[j];
+            }
+            for (; u < n; ++u) {
                 const double wk = wl[u];
                 x = __dadd_rn(__dadd_rn(x, wk), prev);
                 prev = wk;
                 wl[u] = x;
             }
+        }
         __syncwarp();
         for (int u = lane; u < n; u += 32) {
             const int k = c0 + u;
@@ -695,8 +833,17 @@ __device__ __noinline__ bool hf_term_warp(const HfProblem& P, const HfTerm& T, i
             }
         }
         __syncwarp();
-        if (lane == 0)
-            for (int u = 0; u < n; ++u) epart = __dadd_rn(epart, w0[u]);  // (a skipped point adds 0: epart is never -0)
+        if (lane == 0) {  // (a skipped point adds 0: epart is never -0)
+            int u = 0;
+            for (; u + 8 <= n; u += 8) {
+                double a8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a8[j] = w0[u + j];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) epart = __dadd_rn(epart, a8[j]);
+            }
+            for (; u < n; ++u) epart = __dadd_rn(epart, w0[u]);
+        }
         __syncwarp();
     }
     bool ok = true;
@@ -969,17 +1116,26 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
             }
             for (int q = member; q < nstk; q += members) {
                 const int wlo = q + 1 < nstk ? stk_reach_s[cwarp][q + 1] : 0;
-                if (lane == 0) {
-                    int nev = 0, rch = 0;
-                    hf_integ_any<true>(nonrel, stk_e_s[cwarp][q], c, v, xm1, xm2, xkr, r, r2, phi, wlo, ev_idx_s[warp],
-                                       ev_div_s[warp], nev, rch);
-                    nev_s[warp] = nev;
+                // (the warp's scratch: a team's tiles are free by now, the other teams' are not)
+                double* wk = W > 1 ? tiles + member * 160 : hf_dyn_s + warp * 160;
+                int nev = 0;
+                if (P.team_mode == 1 ||
+                    !hf_sweep_write_warp(stk_e_s[cwarp][q], c, v, xm1, xm2, xkr, r, r2, phi, wlo, ev_idx_s[warp], ev_div_s[warp], nev, wk)) {
+                    if (lane == 0) {
+                        int rch = 0;
+                        nev = 0;
+                        hf_integ_any<true>(nonrel, stk_e_s[cwarp][q], c, v, xm1, xm2, xkr, r, r2, phi, wlo, ev_idx_s[warp],
+                                           ev_div_s[warp], nev, rch);
+                        nev_s[warp] = nev;
+                    }
+                    __syncwarp();
+                    nev = nev_s[warp];
                 }
                 __syncwarp();
                 // the rescalings of that sweep: entry j was divided by every later event's p2, in order
-                const int nev = nev_s[warp];
+                // (only up to the last event: the entries beyond belong to other sweeps, which team mates may be writing now)
                 if (nev > 0)
-                    for (int j = wlo + 1 + lane; j <= nr; j += 32) {
+                    for (int j = wlo + 1 + lane, jtop = ev_idx_s[warp][nev - 1]; j <= jtop; j += 32) {
                         double x = phi[j - 1];
                         for (int k = 0; k < nev; ++k)
                             if (ev_idx_s[warp][k] >= j) x = __ddiv_rn(x, ev_div_s[warp][k]);
@@ -1383,7 +1539,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                "replay %.2f (%llu sweeps / %llu orbital solves), tail %.2f, wait for the other CTAs %.2f\n",
                hf_prof_g[0] * 1e-6, hf_prof_g[1] * 1e-6, hf_prof_g[2] * 1e-6, hf_prof_g[8], hf_prof_g[3] * 1e-6, hf_prof_g[4] * 1e-6,
                hf_prof_g[9], hf_prof_g[10], hf_prof_g[5] * 1e-6, hf_prof_g[6] * 1e-6);
-        printf("   blocks of four %llu, with an ordered resolve %llu, with careful steps %llu\n", hf_prof_g[11], hf_prof_g[12], hf_prof_g[13]);
+        printf("   blocks of four %llu, with an ordered resolve %llu, with careful steps %llu; chain %.2f Mcycles\n", hf_prof_g[11], hf_prof_g[12], hf_prof_g[13], hf_prof_g[14] * 1e-6);
         for (int k = 0; k < 16; ++k) hf_prof_g[k] = 0;
 #endif
         P.info[6] = static_cast<double>(t_elsolve);
