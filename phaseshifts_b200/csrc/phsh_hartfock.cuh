@@ -323,11 +323,49 @@ __device__ __forceinline__ void hf_coef(double e, int i, const HfIntegConsts& c,
     dk = __dadd_rn(1.0, __dmul_rn(c.dl2, xk));
 }
 
-// p2/p1 > 1 of the blow-up test (:1108) without the division: for p1 != 0 the correctly rounded quotient exceeds 1 exactly
-// when the operands have one sign and |p2| > |p1| (the next double above |p1| is more than half an ulp of 1 away in ratio)
-__device__ __forceinline__ bool hf_ratio_gt1(double p2, double p1) {
-    if (p1 == 0.0) return __ddiv_rn(p2, p1) > 1.0;
-    return ((p2 > 0.0 && p1 > 0.0) || (p2 < 0.0 && p1 < 0.0)) && fabs(p2) > fabs(p1);
+// The steps of a block of four that hf_team_round's loop does not settle on the spot, one at a time with every test of
+// integ in its place: the end of a sweep (blow-up beyond the turning point, one node too many, the last mesh point), the
+// |p2| > 1e10 rescaling, a table entry outside the fast division's window (y = NaN).  Returns whether the sweep goes on.
+struct HfLane {
+    double p0, p1, A[4], y[4], d[4];
+    float qmin, qmax;
+    int nn, rch, verdict, istop, last, nnideal;
+    bool bad;
+};
+__device__ __noinline__ bool hf_block_slow(HfLane& s, int i0) {
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        const double q = div_fast_finish(__dmul_rn(s.A[k], s.p1), s.d[k], s.y[k]);
+        const float qh = fabsf(__int_as_float(__double2hiint(q)));
+        s.qmin = fminf(s.qmin, qh);
+        s.qmax = fmaxf(s.qmax, qh);
+        double p2 = __dsub_rn(q, s.p0);
+        if (s.y[k] != s.y[k]) {
+            s.bad = true;
+            return false;
+        }
+        if (i > s.istop + 2 && __ddiv_rn(p2, s.p1) > 1.0) {
+            s.verdict = -1;
+            return false;
+        }
+        s.rch = i;
+        if (fabs(p2) > 10000000000.0) {
+            s.p0 = __ddiv_rn(s.p0, p2);
+            s.p1 = __ddiv_rn(s.p1, p2);
+            p2 = __ddiv_rn(p2, p2);
+        }
+        if (__dmul_rn(p2, s.p1) < 0.0) {
+            s.nn = s.nn + 1;
+            if (s.nn > s.nnideal) {
+                s.verdict = 1;
+                return false;
+            }
+        }
+        s.p0 = s.p1;
+        s.p1 = p2;
+        if (i >= s.last) return false;
+    }
+    return true;
 }
 
 // One round of W warps over the energies e (lane = node of the bisection tree, the same in every warp of the team).
@@ -397,55 +435,19 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
     if (blockIdx.x == 0 && threadIdx.x == 0) { hf_prof_g[0] += clock64() - pt0; pt0 = clock64(); }
     long long pwait = 0, pt1 = 0;
 #endif
-    // one step with every test of integ in its place (the rare cases of a block of four, see below)
-    auto careful_step = [&](int i, double A, double y, double dk) {
-        const double q = div_fast_finish(__dmul_rn(A, p1), dk, y);
-        const float qh = fabsf(__int_as_float(__double2hiint(q)));
-        qmin = fminf(qmin, qh);
-        qmax = fmaxf(qmax, qh);
-        double p2 = __dsub_rn(q, p0);
-        if (y != y) {
-            bad = true;
-            active = false;
-        } else if (i > istop + 2 && __ddiv_rn(p2, p1) > 1.0) {
-            verdict = -1;
-            active = false;
-        } else {
-            rch = i;
-            if (fabs(p2) > 10000000000.0) {
-                p0 = __ddiv_rn(p0, p2);
-                p1 = __ddiv_rn(p1, p2);
-                p2 = __ddiv_rn(p2, p2);
-            }
-            if (__dmul_rn(p2, p1) < 0.0) {
-                nn = nn + 1;
-                if (nn > nnideal) {
-                    verdict = 1;
-                    active = false;
-                }
-            }
-            p0 = p1;
-            p1 = p2;
-            if (i >= last) active = false;
-        }
-    };
+    HfLane st;
     for (int k = 0;; ++k) {
         if (role < 0) {
             const double* tile = tiles + static_cast<size_t>(k & 1) * T * kHfEntry + lane;
             const int ibase = 3 + k * T;  // the step that consumes entry s of this tile
             // Four steps at a time.  The recurrence itself runs unconditionally, as one chain of 4 x 5 dependent operations
-            // (a lane that has finished computes on, unheeded); the tests of the four steps become flags, and the ends of a
-            // sweep (blow-up beyond the turning point, one node too many, the last mesh point) are read off the flags in the
-            // order of the steps.  Only what changes the values themselves -- the |p2| > 1e10 rescaling, a table entry
-            // outside the fast division's window -- sends the block through careful_step.
-            double A0 = tile[0], y0 = tile[32], d0 = tile[64];
+            // (a lane that has finished computes on, unheeded); the tests of the four steps become flags, and a block in
+            // which nothing happens -- no end of the sweep, no rescaling, no invalid table entry -- is done with that.
+            // Everything else goes through hf_block_slow, out of line so that it costs the loop no registers.
 #pragma unroll 1
             for (int s0 = 0; s0 < T; s0 += 4) {
                 const double* ent = tile + s0 * kHfEntry;
-#ifdef PHSH_HF_PROFILE
-                long long pb0, pb1;
-                asm volatile("mov.u64 %0, %%clock64;" : "=l"(pb0) : "d"(p1));
-#endif
+                const double A0 = ent[0], y0 = ent[32], d0 = ent[64];
                 const double A1 = ent[kHfEntry], y1 = ent[kHfEntry + 32], d1 = ent[kHfEntry + 64];
                 const double A2 = ent[2 * kHfEntry], y2 = ent[2 * kHfEntry + 32], d2 = ent[2 * kHfEntry + 64];
                 const double A3 = ent[3 * kHfEntry], y3 = ent[3 * kHfEntry + 32], d3 = ent[3 * kHfEntry + 64];
@@ -462,80 +464,47 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
                 const int nc = __dmul_rn(pc, pb) < 0.0 ? 1 : 0;
                 const double qd = div_fast_finish(__dmul_rn(A3, pc), d3, y3);
                 const double pd = __dsub_rn(qd, pb);
-#ifdef PHSH_HF_PROFILE
-                asm volatile("mov.u64 %0, %%clock64;" : "=l"(pb1) : "d"(pd));
-                if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[14] += pb1 - pb0;
-#endif
                 const int nd = __dmul_rn(pd, pc) < 0.0 ? 1 : 0;
                 // (a NaN anywhere -- the y of an invalid entry included -- reaches pd, and fails its comparison)
                 const bool small = fabs(pa) <= big && fabs(pb) <= big && fabs(pc) <= big && fabs(pd) <= big;
                 p0 = pc;
                 p1 = pd;
-                const double Ac = A0, yc = y0, dc = d0;
-                if (s0 + 4 < T) {  // the first entry of the next block, ahead of the tests below
-                    A0 = ent[4 * kHfEntry];
-                    y0 = ent[4 * kHfEntry + 32];
-                    d0 = ent[4 * kHfEntry + 64];
+                // (No divergent branch in what follows: the lanes of a round finish at different times, and a warp that splits
+                // and reconverges in every block pays for it.  The two rare cases are entered by warp votes.)
+                const int i0 = ibase + s0;
+                const int cnt = na + nb + nc + nd;
+                // no step of the block ends the sweep by its node count or is the last one ...
+                bool quiet = small && nn + cnt <= nnideal && i0 + 3 < last;
+                if (__any_sync(0xffffffffu, active && i0 + 3 > istop + 2)) {
+                    // ... or by the blow-up test p2 / p1 > 1 (:1108).  For p1 != 0 the correctly rounded quotient exceeds 1
+                    // exactly when the operands have one sign and |p2| > |p1|: the next double above |p1| is more than half
+                    // an ulp of 1 away in ratio.  (All four quotients are tested, also where the block starts below
+                    // istop + 3: conservative, hf_block_slow decides.)
+                    auto gt1 = [](double p2, double pp) { return ((p2 > 0.0) == (pp > 0.0)) & (fabs(p2) > fabs(pp)); };
+                    const bool calm = (p1s != 0.0) & (pa != 0.0) & (pb != 0.0) & (pc != 0.0) &
+                                      !(gt1(pa, p1s) | gt1(pb, pa) | gt1(pc, pb) | gt1(pd, pc));
+                    quiet = quiet & (calm | (i0 + 3 <= istop + 2));
                 }
-#ifdef PHSH_HF_PROFILE
-                if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[11] += 1;
-#endif
-                if (active) {
-                    const int i0 = ibase + s0;
-                    const float h0 = fabsf(__int_as_float(__double2hiint(qa))), h1 = fabsf(__int_as_float(__double2hiint(qb)));
-                    const float h2 = fabsf(__int_as_float(__double2hiint(qc))), h3 = fabsf(__int_as_float(__double2hiint(qd)));
-                    const bool tail = i0 + 3 > istop + 2;  // some step of the block takes the blow-up test
-                    bool plain = small, quiet = nn + na + nb + nc + nd <= nnideal && i0 + 3 < last;
-                    if (tail) {  // (all four quotients are tested, also where the block starts below istop + 3: conservative)
-                        plain = plain && p1s != 0.0 && pa != 0.0 && pb != 0.0 && pc != 0.0;
-                        auto gt1 = [](double p2, double pp) { return ((p2 > 0.0) == (pp > 0.0)) & (fabs(p2) > fabs(pp)); };
-                        quiet = quiet & !(gt1(pa, p1s) | gt1(pb, pa) | gt1(pc, pb) | gt1(pd, pc));
-                    }
-                    if (plain && quiet) {  // four more steps and nothing happened
-                        nn += na + nb + nc + nd;
-                        rch = i0 + 3;
-                        qmin = fminf(fminf(qmin, fminf(h0, h1)), fminf(h2, h3));
-                        qmax = fmaxf(fmaxf(qmax, fmaxf(h0, h1)), fmaxf(h2, h3));
-                    } else if (plain) {
-#ifdef PHSH_HF_PROFILE
-                        if (blockIdx.x == 0 && threadIdx.x < 32 && (threadIdx.x & 31) == __ffs(__activemask()) - 1) hf_prof_g[12] += 1;
-#endif
-                        bool go = true;
-                        auto resolve = [&](int i, double p2, double pp, float qh, int neg) {
-                            if (!go) return;
-                            qmin = fminf(qmin, qh);
-                            qmax = fmaxf(qmax, qh);
-                            if (i > istop + 2 && hf_ratio_gt1(p2, pp)) {
-                                verdict = -1;
-                                go = false;
-                                return;
-                            }
-                            rch = i;
-                            if (neg) {
-                                nn = nn + 1;
-                                if (nn > nnideal) {
-                                    verdict = 1;
-                                    go = false;
-                                    return;
-                                }
-                            }
-                            if (i >= last) go = false;
-                        };
-                        resolve(i0, pa, p1s, h0, na);
-                        resolve(i0 + 1, pb, pa, h1, nb);
-                        resolve(i0 + 2, pc, pb, h2, nc);
-                        resolve(i0 + 3, pd, pc, h3, nd);
-                        active = go;
-                    } else {
-#ifdef PHSH_HF_PROFILE
-                        if (blockIdx.x == 0 && threadIdx.x < 32 && (threadIdx.x & 31) == __ffs(__activemask()) - 1) hf_prof_g[13] += 1;
-#endif
-                        p0 = p0s;
-                        p1 = p1s;
-                        careful_step(i0, Ac, yc, dc);
-                        if (active) careful_step(i0 + 1, A1, y1, d1);
-                        if (active) careful_step(i0 + 2, A2, y2, d2);
-                        if (active) careful_step(i0 + 3, A3, y3, d3);
+                const bool commit = active & quiet;
+                const float h0 = fabsf(__int_as_float(__double2hiint(qa))), h1 = fabsf(__int_as_float(__double2hiint(qb)));
+                const float h2 = fabsf(__int_as_float(__double2hiint(qc))), h3 = fabsf(__int_as_float(__double2hiint(qd)));
+                const float hlo = fminf(fminf(qmin, fminf(h0, h1)), fminf(h2, h3));
+                const float hhi = fmaxf(fmaxf(qmax, fmaxf(h0, h1)), fmaxf(h2, h3));
+                nn = commit ? nn + cnt : nn;
+                rch = commit ? i0 + 3 : rch;
+                qmin = commit ? hlo : qmin;
+                qmax = commit ? hhi : qmax;
+                if (__any_sync(0xffffffffu, active & !quiet)) {
+                    if (active & !quiet) {
+                        st.p0 = p0s, st.p1 = p1s, st.qmin = qmin, st.qmax = qmax;
+                        st.nn = nn, st.rch = rch, st.verdict = verdict, st.istop = istop, st.last = last, st.nnideal = nnideal;
+                        st.bad = bad;
+                        st.A[0] = A0, st.A[1] = A1, st.A[2] = A2, st.A[3] = A3;
+                        st.y[0] = y0, st.y[1] = y1, st.y[2] = y2, st.y[3] = y3;
+                        st.d[0] = d0, st.d[1] = d1, st.d[2] = d2, st.d[3] = d3;
+                        active = hf_block_slow(st, i0);
+                        p0 = st.p0, p1 = st.p1, qmin = st.qmin, qmax = st.qmax;
+                        nn = st.nn, rch = st.rch, verdict = st.verdict, bad = st.bad;
                     }
                 }
             }
@@ -549,12 +518,14 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
         hf_team_bar(bar_id, nthreads);
 #ifdef PHSH_HF_PROFILE
         pwait += clock64() - pt1;
-        if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[8] += 1;
 #endif
         if (*done == rid) break;
     }
 #ifdef PHSH_HF_PROFILE
-    if (blockIdx.x == 0 && threadIdx.x == 0) { hf_prof_g[1] += clock64() - pt0; hf_prof_g[2] += pwait; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        hf_prof_g[1] += clock64() - pt0;
+        hf_prof_g[2] += pwait;
+    }
 #endif
     if (role < 0) {
         ief = verdict != 2 ? verdict : (nn < nnideal ? -1 : 0);
@@ -1535,11 +1506,10 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         P.info[2] = static_cast<double>(mixing);
         P.info[3] = __ddiv_rn(__dmul_rn(P.scal[1], ratio1), ratio);
 #ifdef PHSH_HF_PROFILE
-        printf("hf profile (Mcycles, CTA 0 warp 0): round prologue %.2f, tiles %.2f (of which barrier wait %.2f), %llu tiles | bisection %.2f, "
+        printf("hf profile (Mcycles, CTA 0 warp 0): round prologue %.2f, tiles %.2f (of which barrier wait %.2f) | bisection %.2f, "
                "replay %.2f (%llu sweeps / %llu orbital solves), tail %.2f, wait for the other CTAs %.2f\n",
-               hf_prof_g[0] * 1e-6, hf_prof_g[1] * 1e-6, hf_prof_g[2] * 1e-6, hf_prof_g[8], hf_prof_g[3] * 1e-6, hf_prof_g[4] * 1e-6,
+               hf_prof_g[0] * 1e-6, hf_prof_g[1] * 1e-6, hf_prof_g[2] * 1e-6, hf_prof_g[3] * 1e-6, hf_prof_g[4] * 1e-6,
                hf_prof_g[9], hf_prof_g[10], hf_prof_g[5] * 1e-6, hf_prof_g[6] * 1e-6);
-        printf("   blocks of four %llu, with an ordered resolve %llu, with careful steps %llu; chain %.2f Mcycles\n", hf_prof_g[11], hf_prof_g[12], hf_prof_g[13], hf_prof_g[14] * 1e-6);
         for (int k = 0; k < 16; ++k) hf_prof_g[k] = 0;
 #endif
         P.info[6] = static_cast<double>(t_elsolve);
