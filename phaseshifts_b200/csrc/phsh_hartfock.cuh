@@ -595,53 +595,114 @@ __device__ __noinline__ bool hf_sweep_write_warp(double e, const HfIntegConsts& 
             sq[lane] = sqrt(__dmul_rn(xm, r[m - 1]));
         }
         __syncwarp();
-        int done = 0, nsteps = 0;  // done: the sweep ended inside this chunk; nsteps: steps of the chunk that store phi
-        if (lane == 0) {
-            for (int L = 0; L < 31; ++L) {
-                const int i = i0 + L;
-                if (i > last) {
-                    done = 1;
-                    break;
-                }
-                const double y = sy[L], dk = sd[L], num = __dmul_rn(sA[L], p1);
-                double q = div_fast_finish(num, dk, y);
-                const float qh = fabsf(__int_as_float(__double2hiint(q)));
-                if (!(y == y && qh >= __int_as_float(0x07f00000) && qh <= __int_as_float(0x77f00000))) q = __ddiv_rn(num, dk);
-                double p2 = __dsub_rn(q, p0);
-                if (i > istop + 2 && __ddiv_rn(p2, p1) > 1.0) {
-                    done = 1;
-                    break;
-                }
-                sp[L] = p2;
-                nsteps = L + 1;
-                if (fabs(p2) > 10000000000.0) {
-                    if (nev < kHfMaxEvents) {
-                        ev_idx[nev] = i;
-                        ev_div[nev] = p2;
-                        ++nev;
-                    } else {
-                        overflow = true;
+        // The steps of the chunk in segments that end with a rescaling (or the chunk): lane 0 runs the bare chain of a
+        // segment, four steps at a time while nothing exceeds 1e10, and leaves p2 of every step in shared memory; the lanes
+        // then evaluate the tests of the steps together (blow-up quotient, node, last point), the warp reads the end of the
+        // sweep off the ballots in the order of the steps, and the lanes store phi of the steps that were taken.
+        const int nmax = min(31, last - i0 + 1);
+        const double big = 10000000000.0;
+        bool done = false;
+        int seg = 0;
+        while (seg < nmax && !done) {
+            int nend = nmax, bigend = 0;
+            double pstart = p1;
+            if (lane == 0) {
+                int L = seg;
+                while (L < nmax) {
+                    if (L + 4 <= nmax) {
+                        const double qa = div_fast_finish(__dmul_rn(sA[L], p1), sd[L], sy[L]);
+                        const double pa = __dsub_rn(qa, p0);
+                        const double qb = div_fast_finish(__dmul_rn(sA[L + 1], pa), sd[L + 1], sy[L + 1]);
+                        const double pb = __dsub_rn(qb, p1);
+                        const double qc = div_fast_finish(__dmul_rn(sA[L + 2], pb), sd[L + 2], sy[L + 2]);
+                        const double pc = __dsub_rn(qc, pa);
+                        const double qd = div_fast_finish(__dmul_rn(sA[L + 3], pc), sd[L + 3], sy[L + 3]);
+                        const double pd = __dsub_rn(qd, pb);
+                        const float h0 = fabsf(__int_as_float(__double2hiint(qa))), h1 = fabsf(__int_as_float(__double2hiint(qb)));
+                        const float h2 = fabsf(__int_as_float(__double2hiint(qc))), h3 = fabsf(__int_as_float(__double2hiint(qd)));
+                        // (a NaN anywhere, an invalid entry's y included, reaches pd and fails its comparison)
+                        if (fabs(pa) <= big && fabs(pb) <= big && fabs(pc) <= big && fabs(pd) <= big &&
+                            fminf(fminf(h0, h1), fminf(h2, h3)) >= __int_as_float(0x07f00000) &&
+                            fmaxf(fmaxf(h0, h1), fmaxf(h2, h3)) <= __int_as_float(0x77f00000)) {
+                            sp[L] = pa;
+                            sp[L + 1] = pb;
+                            sp[L + 2] = pc;
+                            sp[L + 3] = pd;
+                            p0 = pc;
+                            p1 = pd;
+                            L += 4;
+                            continue;
+                        }
                     }
-                    p0 = __ddiv_rn(p0, p2);
-                    p1 = __ddiv_rn(p1, p2);
-                    p2 = __ddiv_rn(p2, p2);
+                    const double y = sy[L], dk = sd[L], num = __dmul_rn(sA[L], p1);
+                    double q = div_fast_finish(num, dk, y);
+                    const float qh = fabsf(__int_as_float(__double2hiint(q)));
+                    if (!(y == y && qh >= __int_as_float(0x07f00000) && qh <= __int_as_float(0x77f00000))) q = __ddiv_rn(num, dk);
+                    const double p2 = __dsub_rn(q, p0);
+                    sp[L] = p2;
+                    if (fabs(p2) > big) {  // the segment ends here; p0, p1 stay those the step started from
+                        nend = L + 1;
+                        bigend = 1;
+                        break;
+                    }
+                    p0 = p1;
+                    p1 = p2;
+                    ++L;
                 }
-                if (__dmul_rn(p2, p1) < 0.0) {
+            }
+            __syncwarp();
+            nend = __shfl_sync(0xffffffffu, nend, 0);
+            bigend = __shfl_sync(0xffffffffu, bigend, 0);
+            pstart = __shfl_sync(0xffffffffu, pstart, 0);
+            // the tests of step i0 + lane (:1106-1131), with the values they see: after the rescaling for the node count
+            bool blow = false, neg = false;
+            if (lane >= seg && lane < nend) {
+                const double p2 = sp[lane], pp = lane == seg ? pstart : sp[lane - 1];
+                blow = i0 + lane > istop + 2 && __ddiv_rn(p2, pp) > 1.0;
+                if (fabs(p2) > big)
+                    neg = __dmul_rn(__ddiv_rn(p2, p2), __ddiv_rn(pp, p2)) < 0.0;
+                else
+                    neg = __dmul_rn(p2, pp) < 0.0;
+            }
+            const unsigned mblow = __ballot_sync(0xffffffffu, blow), mneg = __ballot_sync(0xffffffffu, neg);
+            int nwrite = seg;
+            bool rescale = false;
+            for (int L = seg; L < nend; ++L) {
+                if ((mblow >> L) & 1u) {
+                    done = true;
+                    break;
+                }
+                nwrite = L + 1;
+                if (bigend && L == nend - 1) rescale = true;
+                if ((mneg >> L) & 1u) {
                     nn = nn + 1;
                     if (nn > nnideal) {
-                        done = 1;
+                        done = true;
                         break;
                     }
                 }
-                p0 = p1;
-                p1 = p2;
+                if (i0 + L >= last) {
+                    done = true;
+                    break;
+                }
             }
+            if (lane >= seg && lane < nwrite && i0 + lane > wlo)
+                phi[i0 + lane - 1] = __ddiv_rn(__dmul_rn(sp[lane], sq[lane + 1]), sd[lane + 1]);
+            if (rescale && lane == 0) {
+                const double p2 = sp[nend - 1];
+                if (nev < kHfMaxEvents) {
+                    ev_idx[nev] = i0 + nend - 1;
+                    ev_div[nev] = p2;
+                    ++nev;
+                } else {
+                    overflow = true;
+                }
+                p0 = __ddiv_rn(p1, p2);
+                p1 = __ddiv_rn(p2, p2);
+            }
+            __syncwarp();
+            seg = nend;
         }
-        __syncwarp();
-        done = __shfl_sync(0xffffffffu, done, 0);
-        nsteps = __shfl_sync(0xffffffffu, nsteps, 0);
-        if (lane < nsteps && i0 + lane > wlo) phi[i0 + lane - 1] = __ddiv_rn(__dmul_rn(sp[lane], sq[lane + 1]), sd[lane + 1]);
-        __syncwarp();
         if (done) break;
     }
     overflow = __shfl_sync(0xffffffffu, overflow ? 1 : 0, 0) != 0;
