@@ -37,7 +37,7 @@ constexpr int kHfMaxNr = 4000;    // nrmax
 constexpr int kHfMaxEvents = 64;  // rescalings of one outward sweep kept for the parallel fix-up
 constexpr int kHfMaxStack = 48;   // sweeps of one bisection whose phi entries survive (see elsolve below)
 constexpr int kHfThreads = 768;
-constexpr int kHfMaxCluster = 8;  // CTAs (SMs) that may share one atom
+constexpr int kHfMaxCluster = 16;  // CTAs (SMs) that may share one atom (16: the non-portable size, where a GPC has room)
 constexpr int kHfTeamMaxW = 8;    // warps of one orbital's team when the CTA has warps to spare (see hf_team_round)
 constexpr int kHfEntry = 96;      // doubles of one tabulated mesh point: A, y, dk of 32 energies
 // dynamic shared memory of hartfock_kernel: the coefficient tiles of the teams (2 buffers x 4 mesh points per producer

@@ -91,13 +91,13 @@ def test_batch_of_several_atoms_in_one_launch(hio):
 
 
 def test_results_do_not_depend_on_the_cluster_size(hio, monkeypatch):
-    """One atom may be shared by the 1, 2, 4 or 8 CTAs of a thread-block cluster (orbitals and pair terms dealt round robin,
+    """One atom may be shared by the 1, 2, 4, 8 or 16 CTAs of a thread-block cluster (orbitals and pair terms dealt round robin,
     exchange through global memory at cluster barriers): eigenvalues, charge density and iteration count must be the same
     bits whatever the size, and equal to the oracle's."""
     from phaseshifts_b200 import api
     atoms = [dict(z=6, nr=1000, rel=1.0, orbitals=C_ORB), dict(z=3, nr=800, rel=0.0, orbitals=[(1, 0, 0, -0.5, 1, 2.0), (2, 0, 0, -0.5, 1, 1.0)])]
     want = [_oracle(hio, a["z"], a["nr"], a["rel"], 0.0, 0, a["orbitals"]) for a in atoms]
-    for c in (1, 2, 4, 8):
+    for c in (1, 2, 4, 8, 16):  # (16 is the non-portable size: taken where a GPC has room, else the launch falls back)
         monkeypatch.setenv("PHSH_B200_HARTFOCK_CLUSTER", str(c))
         got = api.hartfock_batch(atoms)
         for g, w in zip(got, want):
