@@ -1178,13 +1178,23 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
             if (W > 1) {
                 __threadfence_block();  // phi is global memory: the consumer reads what its team mates wrote
                 hf_team_bar(1 + team, 32 * members);
-                if (!consumer) continue;
             }
+            // what is left of the orbital -- augment, norm, kinetic energy -- by the whole team: element-wise loops over all its
+            // lanes, the two sums in the Fortran's order by the first
+            const int tl = member * 32 + lane, tn = members * 32;
+            auto tsync = [&] {
+                if (W > 1) {
+                    __threadfence_block();
+                    hf_team_bar(1 + team, 32 * members);
+                } else {
+                    __syncwarp();
+                }
+            };
 #ifdef PHSH_HF_PROFILE
             if (blockIdx.x == 0 && threadIdx.x == 0) hf_prof_g[4] += clock64() - pk0;
             pk0 = clock64();
 #endif
-            if (lane == 0) {
+            if (tl == 0) {
                 P.evnew[o] = e_last;
                 P.statusd[o] = static_cast<double>(status);
             }
@@ -1194,7 +1204,7 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                     // augment (:796-841)
                     const double cc = __dmul_rn(cl, cl);
                     const double c2 = __dadd_rn(cc, cc);
-                    for (int j = 1 + lane; j <= nr; j += 32) {
+                    for (int j = 1 + tl; j <= nr; j += tn) {
                         double out = 0.0;  // phi2(nr-2..nr) is never assigned by the Fortran: a fresh work array holds 0
                         if (j >= 4 && j <= nr - 3) {
                             if (phi[j - 1] != 0.0) {
@@ -1217,36 +1227,36 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                         }
                         phi2[j - 1] = out;
                     }
-                    __syncwarp();
-                    if (lane < 3) phi2[lane] = __ddiv_rn(__dmul_rn(phi[lane], phi[3]), phi2[3]);
-                    __syncwarp();
-                    for (int j = lane; j < nr; j += 32) phi[j] = phi2[j];
-                    __syncwarp();
+                    tsync();
+                    if (tl < 3) phi2[tl] = __ddiv_rn(__dmul_rn(phi[tl], phi[3]), phi2[3]);
+                    tsync();
+                    for (int j = tl; j < nr; j += tn) phi[j] = phi2[j];
+                    tsync();
                 }
                 // the terms by all lanes, their sum in the Fortran's order by one
-                for (int j = lane; j < nr; j += 32) phi2[j] = __dmul_rn(__dmul_rn(phi[j], phi[j]), dr[j]);
-                __syncwarp();
-                if (lane == 0) {
+                for (int j = tl; j < nr; j += tn) phi2[j] = __dmul_rn(__dmul_rn(phi[j], phi[j]), dr[j]);
+                tsync();
+                if (tl == 0) {
                     double s = 0.0;
                     for (int j = 0; j < nr; ++j) s = __dadd_rn(s, phi2[j]);
                     xnorm_s[o] = sqrt(s);
                 }
-                __syncwarp();
+                tsync();
                 const double xnorm = xnorm_s[o];
-                for (int j = lane; j < nr; j += 32) phi[j] = __ddiv_rn(phi[j], xnorm);
-                __syncwarp();
+                for (int j = tl; j < nr; j += tn) phi[j] = __ddiv_rn(phi[j], xnorm);
+                tsync();
             }
             // kinetic energy (:416-427)
             {
                 const double evi = e_last;
                 const double* orb = P.orb + static_cast<long>(o) * nr;
-                for (int j = nr - lane; j >= 1; j -= 32) {  // ll = 2, 4, 2, ... from j = nr downwards
+                for (int j = nr - tl; j >= 1; j -= tn) {  // ll = 2, 4, 2, ... from j = nr downwards
                     const double dq = __dmul_rn(phi[j - 1], phi[j - 1]);
                     const double ll = ((nr - j) & 1) ? 4.0 : 2.0;
                     phi2[j - 1] = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dsub_rn(evi, orb[j - 1]), dr[j - 1]), dq), ll), 3.0);
                 }
-                __syncwarp();
-                if (lane == 0) {
+                tsync();
+                if (tl == 0) {
                     double ekk = 0.0;
                     for (int j = nr; j >= 1; --j) ekk = __dadd_rn(ekk, phi2[j - 1]);
                     P.ek[o] = ekk;
