@@ -371,14 +371,13 @@ __device__ __noinline__ bool hf_block_slow(HfLane& s, int i0) {
 // One round of W warps over the energies e (lane = node of the bisection tree, the same in every warp of the team).
 // role < 0: consumer, else producer number role of NP.  `tiles`: this team's 2 x 4 NP x kHfEntry doubles;
 // `done`: this team's flag word in shared memory; rid: a number no earlier round of this team used.
+// (three functions, each with the registers it needs: the consumer's loop must not carry the producers' pointers)
 template <bool NONREL>
-__device__ __noinline__ void hf_team_round(double e, bool reachable, const HfIntegConsts& c, const double* __restrict__ v,
-                                           const double* __restrict__ xm1, const double* __restrict__ xm2,
-                                           const double* __restrict__ xkr, const double* __restrict__ r,
-                                           const double* __restrict__ r2, double* tiles, volatile int* done, int rid, int NP,
-                                           int role, int bar_id, bool force_exact, int& ief, int& reach) {
-    const int lane = threadIdx.x & 31, nr = c.nr, nnideal = c.nnideal;
-    int rch = 2;  // the sweep's reach (a local: the reference would live in memory)
+__device__ __noinline__ void hf_team_producer(double e, bool reachable, const HfIntegConsts& c, const double* __restrict__ v,
+                                              const double* __restrict__ xm1, const double* __restrict__ xm2,
+                                              const double* __restrict__ xkr, const double* __restrict__ r2, double* tiles,
+                                              volatile int* done, int rid, int NP, int role, int bar_id) {
+    const int lane = threadIdx.x & 31, nr = c.nr;
     const int T = 4 * NP, nthreads = 32 * (NP + 1);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     auto produce = [&](int k) {
@@ -402,42 +401,36 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
             ent[64 + lane] = dk;
         }
     };
-    // the consumer lane's sweep
-    double p0 = 0.0, p1 = 0.0;
-    int nn = 0, istop = 0, last = 0, verdict = 2;
-    bool active = false, bad = false;
-    float qmin = __int_as_float(0x7f000000), qmax = 0.0f;
-#ifdef PHSH_HF_PROFILE
-    long long pt0 = clock64();
-#endif
-    if (role < 0) {
-        if (reachable) {
-            DivTrack unused;
-            double xk0, dk0, xm0, xk2, dk2, xmm;
-            hf_coef<false, true>(e, 1, c, v, xm1, xm2, xkr, r2, xk0, dk0, xm0, unused);
-            hf_coef<false, true>(e, 2, c, v, xm1, xm2, xkr, r2, xk2, dk2, xmm, unused);
-            p0 = dk0;
-            p1 = __dmul_rn(__dmul_rn(dk2, __dsub_rn(c.pw12, __ddiv_rn(__dmul_rn(__dsub_rn(r[1], r[0]), c.z), c.xlp))),
-                           sqrt(__ddiv_rn(xm0, xmm)));
-            istop = hf_turning_point(e, c.vsm, nr);
-            if (istop == 0) {
-                verdict = -1;
-            } else {
-                active = true;
-                last = max(min(istop + 2, nr), nr - 1);
-            }
-        }
-    } else {
-        produce(0);
-    }
+    produce(0);
     hf_team_bar(bar_id, nthreads);
-#ifdef PHSH_HF_PROFILE
-    if (blockIdx.x == 0 && threadIdx.x == 0) { hf_prof_g[0] += clock64() - pt0; pt0 = clock64(); }
-    long long pwait = 0, pt1 = 0;
-#endif
+    for (int k = 0;; ++k) {
+        produce(k + 1);
+        hf_team_bar(bar_id, nthreads);
+        if (*done == rid) break;
+    }
+}
+
+// the consumer lane's sweep from its start values p0, p1 (0 / inactive if the lane has no sweep to run)
+struct HfSweepState {
+    double p0, p1;
+    float qmin, qmax;
+    int nn, istop, last, verdict, rch;
+    bool active, bad;
+};
+__device__ __noinline__ void hf_team_consumer(HfSweepState& S, int nnideal, const double* tiles, volatile int* done, int rid, int NP,
+                                              int bar_id, bool force_exact) {
+    const int lane = threadIdx.x & 31;
+    const int T = 4 * NP, nthreads = 32 * (NP + 1);
+    double p0 = S.p0, p1 = S.p1;
+    float qmin = S.qmin, qmax = S.qmax;
+    int nn = S.nn, verdict = S.verdict, rch = S.rch;
+    const int istop = S.istop, last = S.last;
+    bool active = S.active, bad = S.bad;
+    (void)force_exact;
+    hf_team_bar(bar_id, nthreads);
     HfLane st;
     for (int k = 0;; ++k) {
-        if (role < 0) {
+        {
             const double* tile = tiles + static_cast<size_t>(k & 1) * T * kHfEntry + lane;
             const int ibase = 3 + k * T;  // the step that consumes entry s of this tile
             // Four steps at a time.  The recurrence itself runs unconditionally, as one chain of 4 x 5 dependent operations
@@ -508,38 +501,60 @@ __device__ __noinline__ void hf_team_round(double e, bool reachable, const HfInt
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, active) && lane == 0) *done = rid;
-        } else {
-            produce(k + 1);
         }
-#ifdef PHSH_HF_PROFILE
-        pt1 = clock64();
-#endif
+        if (!__any_sync(0xffffffffu, active) && lane == 0) *done = rid;
         hf_team_bar(bar_id, nthreads);
-#ifdef PHSH_HF_PROFILE
-        pwait += clock64() - pt1;
-#endif
         if (*done == rid) break;
     }
-#ifdef PHSH_HF_PROFILE
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        hf_prof_g[1] += clock64() - pt0;
-        hf_prof_g[2] += pwait;
+    S.p0 = p0, S.p1 = p1, S.qmin = qmin, S.qmax = qmax;
+    S.nn = nn, S.verdict = verdict, S.rch = rch, S.active = active, S.bad = bad;
+}
+
+template <bool NONREL>
+__device__ __forceinline__ void hf_team_round(double e, bool reachable, const HfIntegConsts& c, const double* __restrict__ v,
+                                              const double* __restrict__ xm1, const double* __restrict__ xm2,
+                                              const double* __restrict__ xkr, const double* __restrict__ r,
+                                              const double* __restrict__ r2, double* tiles, volatile int* done, int rid, int NP,
+                                              int role, int bar_id, bool force_exact, int& ief, int& reach) {
+    if (role >= 0) {
+        hf_team_producer<NONREL>(e, reachable, c, v, xm1, xm2, xkr, r2, tiles, done, rid, NP, role, bar_id);
+        return;
     }
-#endif
-    if (role < 0) {
-        ief = verdict != 2 ? verdict : (nn < nnideal ? -1 : 0);
-        reach = rch;
-        if (!(qmin >= __int_as_float(0x07f00000) && qmax <= __int_as_float(0x77f00000))) bad = true;
-        if (reachable && (bad || force_exact)) {
-            int nev = 0;
-            bool ok = true;
-            ief = hf_integ<false, true, false>(e, c, v, xm1, xm2, xkr, r, r2, nullptr, 0, nullptr, nullptr, nev, reach, ok);
+    const int nr = c.nr, nnideal = c.nnideal;
+    HfSweepState S;
+    S.p0 = S.p1 = 0.0;
+    S.qmin = __int_as_float(0x7f000000);
+    S.qmax = 0.0f;
+    S.nn = 0, S.istop = 0, S.last = 0, S.verdict = 2, S.rch = 2;
+    S.active = false, S.bad = false;
+    if (reachable) {
+        DivTrack unused;
+        double xk0, dk0, xm0, xk2, dk2, xmm;
+        hf_coef<false, true>(e, 1, c, v, xm1, xm2, xkr, r2, xk0, dk0, xm0, unused);
+        hf_coef<false, true>(e, 2, c, v, xm1, xm2, xkr, r2, xk2, dk2, xmm, unused);
+        S.p0 = dk0;
+        S.p1 = __dmul_rn(__dmul_rn(dk2, __dsub_rn(c.pw12, __ddiv_rn(__dmul_rn(__dsub_rn(r[1], r[0]), c.z), c.xlp))),
+                         sqrt(__ddiv_rn(xm0, xmm)));
+        S.istop = hf_turning_point(e, c.vsm, nr);
+        if (S.istop == 0) {
+            S.verdict = -1;
+        } else {
+            S.active = true;
+            S.last = max(min(S.istop + 2, nr), nr - 1);
         }
-        if (!reachable) {
-            ief = 0;
-            reach = 0;
-        }
+    }
+    hf_team_consumer(S, nnideal, tiles, done, rid, NP, bar_id, force_exact);
+    ief = S.verdict != 2 ? S.verdict : (S.nn < nnideal ? -1 : 0);
+    reach = S.rch;
+    if (!(S.qmin >= __int_as_float(0x07f00000) && S.qmax <= __int_as_float(0x77f00000))) S.bad = true;
+    if (reachable && (S.bad || force_exact)) {
+        int nev = 0;
+        bool ok = true;
+        ief = hf_integ<false, true, false>(e, c, v, xm1, xm2, xkr, r, r2, nullptr, 0, nullptr, nullptr, nev, reach, ok);
+    }
+    if (!reachable) {
+        ief = 0;
+        reach = 0;
     }
 }
 
