@@ -96,6 +96,7 @@ struct HfProblem {  // one atom; every pointer is a DEVICE pointer into this ato
     const HfTerm* terms;
     const int* upd_off;   // [nel+1]
     const int* upd;       // entries term*2+slot, per orbital in application order
+    const int* order;     // [nterms] the terms sorted by kind: which term the n-th thread (or warp) takes
     double *rho, *ev, *ek;  // outputs [nr], [nel], [nel]
     double* info;           // [8] etot, iterations, status, eerror ...
     double* history;        // [2*max_iter]
@@ -1430,7 +1431,8 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
                     hf_term_warp<false>(P, T, t, sm, etot_part);
             }
         } else {
-            for (int t = tid_l * csize + crank; t < P.nterms; t += nth) {
+            for (int n = tid_l * csize + crank; n < P.nterms; n += nth) {
+                const int t = P.order[n];
                 const HfTerm T = P.terms[t];
                 if (!(P.rpinv_ok && scan_term(T, t, std::true_type()))) scan_term(T, t, std::false_type());
             }
