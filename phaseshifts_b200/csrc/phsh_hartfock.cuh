@@ -1023,7 +1023,16 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         const int role = consumer ? -1 : wt - 1 - (W == 8 && wt > 4 ? 1 : 0);
         const int cwarp = team * W, members = NP + 1, member = role + 1;
         double* tiles = hf_dyn_s + static_cast<size_t>(team) * 2 * 4 * NP * kHfEntry;
-        for (int o = idle ? nel : crank + csize * team; o < nel; o += csize * nteams) {
+        // Orbitals are dealt round robin over the CTAs and their teams -- except where the cluster has more than half as many
+        // CTAs as the atom has orbitals: then the innermost orbitals, whose sweeps are the shortest, share CTAs two by two and
+        // each of the others has a CTA (and its consumer a scheduler) to itself.
+        int o_first = crank + csize * team, o_step = csize * nteams;
+        if (W > 1 && nel > csize && nel <= 2 * csize) {
+            const int shared = nel - csize;  // CTAs that take two orbitals
+            o_first = crank < shared ? (team < 2 ? 2 * crank + team : nel) : (team == 0 ? shared + crank : nel);
+            o_step = nel;
+        }
+        for (int o = idle ? nel : o_first; o < nel; o += o_step) {
             const double* v = P.v + static_cast<long>(o) * nr;
             const double* xm1 = P.xm1 + static_cast<long>(o) * nr;
             const double* xm2 = P.xm2 + static_cast<long>(o) * nr;
