@@ -4,8 +4,10 @@
 // elsolve :742-793, augment :796-841, setqmm :844-931, integ :992-1165, the density of hfdisk :1889-1896; driven from
 // phaseshifts/atorb.py:1095-1209.  The whole self-consistency loop of one atom runs inside ONE kernel launch.
 //
-// Design.  One CTA per atom (a batch = the elements of a structure, or of many).  The reference is a strictly serial
-// program; what parallelism it has is
+// Design.  One CTA per atom when the batch fills the GPU (a batch = the elements of a structure, or of many), a thread-
+// block cluster of 2, 4, 8 or 16 CTAs per atom when it does not (the host picks the largest size whose clusters are all
+// resident; orbitals and pair terms are dealt over the CTAs, which meet at cluster barriers).  The reference is a strictly
+// serial program; what parallelism it has is
 //   * the orbitals of one SCF iteration are independent (22 for Re): one WARP per orbital;
 //   * elsolve finds each eigenvalue by ~46 bisection steps, each an outward Numerov sweep whose outcome is one of
 //     {too low, too high, converged}: the 31 energies of the next FIVE bisection levels are a fixed binary tree of
@@ -14,6 +16,10 @@
 //   * getpot's radial integrals are running sums along r (order matters for bits), but independent between the ~700
 //     (orbital pair, multipole) terms: one THREAD per term scans r and stores its contribution, then one thread per
 //     (orbital, r) adds the contributions in the reference's order of the pair loops.
+// Where a CTA has more warps than work of that shape, the same operations are arranged for latency instead (sections
+// "team sweeps", "the replayed sweep, by a whole warp" and "getpot, one WARP per term" below): a team of warps per
+// orbital with producers of the sweep coefficients and one consumer of the bare recurrence, the owning sweeps replayed
+// in parallel by whole warps, a warp per pair term.
 // Everything order-dependent keeps the reference's order, every operation is the IEEE double operation of the Fortran
 // statement (file compiled with -fmad=false, __ddiv_rn, correctly rounded sqrt), and every transcendental of the
 // Hartree-Fock path (the log grid, r**k, the power-law start of integ) is tabulated on the host with libm: the
