@@ -95,7 +95,12 @@ def test_results_do_not_depend_on_the_cluster_size(hio, monkeypatch):
     exchange through global memory at cluster barriers): eigenvalues, charge density and iteration count must be the same
     bits whatever the size, and equal to the oracle's."""
     from phaseshifts_b200 import api
-    atoms = [dict(z=6, nr=1000, rel=1.0, orbitals=C_ORB), dict(z=3, nr=800, rel=0.0, orbitals=[(1, 0, 0, -0.5, 1, 2.0), (2, 0, 0, -0.5, 1, 1.0)])]
+    cu_orb = [(1, 0, 0, -0.5, 1, 2.0), (2, 0, 0, -0.5, 1, 2.0), (2, 1, 1, -0.5, 1, 2.0), (2, 1, 1, -1.5, 1, 4.0),
+              (3, 0, 0, -0.5, 1, 2.0), (3, 1, 1, -0.5, 1, 2.0), (3, 1, 1, -1.5, 1, 4.0), (3, 2, 2, -1.5, 1, 4.0),
+              (3, 2, 2, -2.5, 1, 6.0), (4, 0, 0, -0.5, 1, 1.0)]
+    # (ten orbitals on eight CTAs: the case in which the innermost orbitals share CTAs two by two and the others have one each)
+    atoms = [dict(z=6, nr=1000, rel=1.0, orbitals=C_ORB), dict(z=3, nr=800, rel=0.0, orbitals=[(1, 0, 0, -0.5, 1, 2.0), (2, 0, 0, -0.5, 1, 1.0)]),
+             dict(z=29, nr=700, rel=1.0, orbitals=cu_orb)]
     want = [_oracle(hio, a["z"], a["nr"], a["rel"], 0.0, 0, a["orbitals"]) for a in atoms]
     for c in (1, 2, 4, 8, 16):  # (16 is the non-portable size: taken where a GPC has room, else the launch falls back)
         monkeypatch.setenv("PHSH_B200_HARTFOCK_CLUSTER", str(c))
