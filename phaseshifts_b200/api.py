@@ -568,7 +568,8 @@ def selftest_cavpot(n=1 << 22, seed=1, device=0):
 
 
 def hartfock_batch(atoms, *, history_cap=64, asbuilt=False, device=0):
-    """Self-consistent atomic charge densities for a batch of atoms (``libphsh.f:60-2068``, one CTA per atom).
+    """Self-consistent atomic charge densities for a batch of atoms (``libphsh.f:60-2068``; one CTA per atom, or a thread-block cluster
+    of up to sixteen CTAs per atom when the batch is small).
 
     ``atoms``: list of dicts ``z, nr[, rel=1, alfa=0, iuflag=0, ratio=0.5, etol=0.0005, xnum=100], orbitals`` with
     ``orbitals`` = rows ``(n, l, m, -j, spin, occupation)`` as in the records of hartfock's ``a`` command.
