@@ -1609,10 +1609,9 @@ __global__ void __launch_bounds__(kHfThreads, 1) hartfock_kernel(const HfProblem
         P.info[2] = static_cast<double>(mixing);
         P.info[3] = __ddiv_rn(__dmul_rn(P.scal[1], ratio1), ratio);
 #ifdef PHSH_HF_PROFILE
-        printf("hf profile (Mcycles, CTA 0 warp 0): round prologue %.2f, tiles %.2f (of which barrier wait %.2f) | bisection %.2f, "
-               "replay %.2f (%llu sweeps / %llu orbital solves), tail %.2f, wait for the other CTAs %.2f\n",
-               hf_prof_g[0] * 1e-6, hf_prof_g[1] * 1e-6, hf_prof_g[2] * 1e-6, hf_prof_g[3] * 1e-6, hf_prof_g[4] * 1e-6,
-               hf_prof_g[9], hf_prof_g[10], hf_prof_g[5] * 1e-6, hf_prof_g[6] * 1e-6);
+        printf("hf profile (Mcycles, CTA 0 warp 0): bisection %.2f, replay %.2f (%llu sweeps / %llu orbital solves), tail %.2f, "
+               "wait for the other CTAs %.2f\n",
+               hf_prof_g[3] * 1e-6, hf_prof_g[4] * 1e-6, hf_prof_g[9], hf_prof_g[10], hf_prof_g[5] * 1e-6, hf_prof_g[6] * 1e-6);
         for (int k = 0; k < 16; ++k) hf_prof_g[k] = 0;
 #endif
         P.info[6] = static_cast<double>(t_elsolve);
