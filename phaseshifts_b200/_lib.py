@@ -107,6 +107,8 @@ _SIGNATURES = {
                                                 C.c_int, C.c_int]),
     "phsh_b200_hartfock_file": (C.c_int, [C.c_char_p, C.POINTER(FileOpts)]),
     "phsh_b200_selftest_cavpot": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),
+    "phsh_b200_selftest_hartfock": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong),
+                                              C.c_int]),
     "phsh_b200_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "phsh_b200_selftest_div075": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_int]),
     "phsh_b200_selftest_divfast": (C.c_int, [C.c_long, C.c_ulonglong, C.POINTER(C.c_ulonglong),

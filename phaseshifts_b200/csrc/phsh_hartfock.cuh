@@ -130,6 +130,76 @@ __device__ __forceinline__ int hf_turning_point(double e, const double* __restri
     return lo;
 }
 
+// Self test of two shortcuts of this file against what they replace, on pseudo-random inputs (one case per thread):
+//  * hf_turning_point (bisection over suffix minima) vs the Fortran's downward scan, on potentials that are NOT monotone,
+//    hold runs of equal values, infinities and the occasional NaN, for energies at, between and beyond the values;
+//  * div_fast_rcp + div_fast_finish (the reciprocal tabulated by producers, the quotient finished by the consumer) vs the
+//    IEEE division, wherever the validity window of the fast path says it may be used.
+__global__ void hartfock_selftest_kernel(unsigned long long seed, long n, unsigned long long* mismatches) {
+    const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long w = seed + 0x9E3779B97F4A7C15ULL * static_cast<unsigned long long>(i + 1);
+    auto next = [&]() {
+        w += 0x9E3779B97F4A7C15ULL;
+        unsigned long long z = w;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    };
+    constexpr int NR = 48;
+    double v[NR], sm[NR];
+    const int nr = 3 + static_cast<int>(next() % (NR - 2));
+    const int mode = static_cast<int>(next() % 4);
+    double base = -50.0;
+    for (int j = 0; j < nr; ++j) {
+        const unsigned long long r = next();
+        double x;
+        if (mode == 0) x = base + static_cast<double>(r % 1000) * 0.1;                         // random walk upwards with dips
+        else if (mode == 1) x = static_cast<double>(static_cast<long long>(r % 7)) - 3.0;       // few distinct values: ties
+        else if (mode == 2) x = -1.0 / (1.0 + j) + ((r & 15) == 0 ? 5.0 : 0.0);                 // monotone with spikes
+        else x = static_cast<double>(static_cast<long long>(r % 2001)) * 0.01 - 10.0;           // noise
+        if ((r >> 40) % 97 == 0) x = __longlong_as_double(0x7ff8000000000000LL);                // NaN
+        if ((r >> 48) % 89 == 0) x = __longlong_as_double((r & 1) ? 0x7ff0000000000000LL : 0xfff0000000000000LL);
+        v[j] = x;
+        base += static_cast<double>(r % 5) * 0.5 - 0.5;
+    }
+    double mn = __longlong_as_double(0x7ff0000000000000LL);
+    sm[nr - 1] = mn;
+    for (int j = nr - 1; j >= 1; --j) {
+        const double vj = v[j - 1];
+        mn = vj < mn ? vj : mn;
+        sm[j - 1] = mn;
+    }
+    for (int t = 0; t < 8; ++t) {
+        const unsigned long long r = next();
+        double e = v[r % nr];
+        if (t & 1) e = e + (static_cast<double>((r >> 20) % 3) - 1.0) * 1e-9;
+        if (t == 6) e = 1e30;
+        if (t == 7) e = -1e30;
+        int want = 0;
+        for (int j = nr - 1; j >= 2; --j)
+            if (e > v[j - 1]) {
+                want = j;
+                break;
+            }
+        if (hf_turning_point(e, sm, nr) != want) atomicAdd(mismatches, 1ULL);
+    }
+    // the split fast division: divisor exponent in [-10, 18], numerator's in [-920, 920] (straddles every edge of the window)
+    for (int t = 0; t < 4; ++t) {
+        const unsigned long long za = next(), zx = next();
+        const unsigned long long ea = 1023ull - 10ull + ((za >> 52) & 0x7ffull) % 29ull;
+        const unsigned long long ex = 1023ull - 920ull + ((zx >> 52) & 0x7ffull) % 1841ull;
+        const double a = __longlong_as_double(static_cast<long long>((za & 0x800FFFFFFFFFFFFFULL) | (ea << 52)));
+        const double x = __longlong_as_double(static_cast<long long>((zx & 0x800FFFFFFFFFFFFFULL) | (ex << 52)));
+        const double q = div_fast_finish(x, a, div_fast_rcp(a));
+        const float qh = fabsf(__int_as_float(__double2hiint(q))), ah = fabsf(__int_as_float(__double2hiint(a)));
+        const bool may = qh >= __int_as_float(0x07f00000) && qh <= __int_as_float(0x77f00000) &&
+                         ah >= __int_as_float(0x3f700000) && ah <= __int_as_float(0x40f00000);
+        if (may && __double_as_longlong(q) != __double_as_longlong(__ddiv_rn(x, a))) atomicAdd(mismatches, 1ULL);
+        if (may) atomicAdd(mismatches + 1, 1ULL);
+    }
+}
+
 // integ (libphsh.f:992-1165) with istop = 0 on entry.  Returns the verdict (ief after elsolve's node-count override,
 // :763) and, in `reach`, the last index of phi the sweep assigns.  WRITE = true also stores phi(wlo+1 .. reach) -- the
 // entries no later sweep of the bisection overwrites -- with the |p2| > 1e10 rescalings recorded so that the warp can

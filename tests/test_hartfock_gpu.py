@@ -128,6 +128,19 @@ def test_results_do_not_depend_on_how_the_sweeps_are_run(hio, monkeypatch):
                 assert np.array_equal(g["rho"], w["rho"]) and np.array_equal(g["ev"][: len(w["ev"])], w["ev"]), (mode, c)
 
 
+def test_shortcuts_of_the_atomic_step_selftest():
+    """integ's turning point by bisection over suffix minima against the Fortran's downward scan (non-monotone potentials,
+    ties, infinities, NaNs) and the fast division split into reciprocal and finish against the IEEE division, on the device."""
+    import ctypes
+    from phaseshifts_b200 import _lib
+    lib = _lib.load()
+    for seed in (1, 20261020):
+        bad, used = ctypes.c_ulonglong(1), ctypes.c_ulonglong(0)
+        _lib.check(lib.phsh_b200_selftest_hartfock(2_000_000, seed, ctypes.byref(bad), ctypes.byref(used), 0))
+        assert bad.value == 0
+        assert used.value > 1_000_000  # the window was exercised
+
+
 def test_shell_averaging_and_local_exchange_modes(hio):
     from phaseshifts_b200 import api
     for iuflag in (1, 2):
